@@ -1,0 +1,175 @@
+"""Tensor collectives on the P2P kernels: allgather, allreduce, broadcast, pad-to-max.
+
+Each function takes ONE contiguous CUDA tensor and follows the reference's per-leaf semantics
+(``src/accelerate/utils/operations.py``): ``gather`` allocates and concatenates on dim 0
+(:316-352), ``reduce`` never mutates its input and divides only for "mean" (:839-878),
+``broadcast`` writes in place (:520-525), ``pad_across_processes`` returns the *same object* when
+no padding is needed (:743-796).  Data moves through the symmetric staging segment:
+
+    stage (b200dp_pack, one launch)  ->  peers pull / reduce over NVLink (one launch)
+
+so a small gather costs two launches and zero NCCL calls.  Tensors larger than the staging
+segment are processed in chunks.
+"""
+
+from __future__ import annotations
+
+import torch
+
+from . import native
+from .runtime import SymmRuntime, native_dtype
+
+# below this many bytes per rank the out-of-place one-shot allreduce wins (latency bound)
+ONESHOT_MAX_BYTES = 512 * 1024
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check_cuda(t: torch.Tensor, rt: SymmRuntime, op: str):
+    if t.device != rt.device:
+        raise RuntimeError(
+            f"{op}: tensor is on {t.device} but this process drives {rt.device}; move it there first "
+            "(there is no CPU fallback for the CUDA collectives)"
+        )
+
+
+def all_gather(t: torch.Tensor) -> torch.Tensor:
+    """out[r*b:(r+1)*b] = rank r's tensor; 0-dim inputs become shape [N]. Bit-exact, any dtype."""
+    rt = SymmRuntime.get()
+    _check_cuda(t, rt, "gather")
+    if t.ndim == 0:
+        t = t.clone()[None]
+    if not t.is_contiguous():
+        t = t.contiguous()
+    world = rt.world
+    out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    nbytes = t.numel() * t.element_size()
+    if nbytes == 0:
+        return out
+    staging = rt.ensure_staging()
+    st = _stream()
+    cap = staging.nbytes // 16 * 16
+    src, dst = t.data_ptr(), out.data_ptr()
+    done = 0
+    while done < nbytes:
+        n = min(cap, nbytes - done)
+        rt.ctx.pack([src + done], [staging.ptr], [n], rt.use_bulk_pack, st)
+        rt.ctx.pull(staging.seg, 0, n, dst + done, nbytes, 0, world, native.CH_USER, 0, st)
+        done += n
+    return out
+
+
+def all_reduce(t: torch.Tensor, mean: bool = False) -> torch.Tensor:
+    """Return sum over ranks of ``t`` (a fresh tensor; ``t`` is untouched), divided by N if ``mean``."""
+    rt = SymmRuntime.get()
+    _check_cuda(t, rt, "reduce")
+    world = rt.world
+    src = t if t.is_contiguous() else t.contiguous()
+    dt = native_dtype(src.dtype)
+    if dt is None:
+        raise TypeError(f"reduce: dtype {src.dtype} is not supported by the P2P allreduce kernels")
+    if src.dtype in (torch.bool, torch.int8):
+        raise TypeError(f"reduce: dtype {src.dtype} has no well-defined sum")
+    out = torch.empty_like(src)
+    numel, es = src.numel(), src.element_size()
+    if numel == 0:
+        return out
+    if mean and not src.is_floating_point():
+        # reference: `cloned_tensor /= N` raises for integer tensors
+        raise RuntimeError("result type Float can't be cast to the desired output type " + str(src.dtype))
+    staging = rt.ensure_staging()
+    st = _stream()
+    nbytes = numel * es
+    divisor = float(world) if mean else 1.0
+    fused_types = (torch.float32, torch.bfloat16, torch.float16)
+    cap_elems = (staging.nbytes // 16 * 16) // es
+    large = nbytes > ONESHOT_MAX_BYTES and src.dtype in fused_types
+    done = 0
+    while done < numel:
+        n = min(cap_elems, numel - done)
+        nb = n * es
+        rt.ctx.pack([src.data_ptr() + done * es], [staging.ptr], [nb], rt.use_bulk_pack, st)
+        if not large:
+            rt.ctx.allreduce_oneshot(staging.seg, 0, n, dt, divisor, out.data_ptr() + done * es, native.CH_USER, 0, st)
+        else:
+            # two-shot / NVLS in place on the staging copy, then one copy out
+            padded = (nb + 15) // 16 * 16 // es
+            rt.ctx.allreduce_bucket(staging.seg, 0, padded, dt, 1.0, -1, 0, native.ALGO_AUTO if staging.multicast
+                                    else native.ALGO_TWOSHOT, native.CH_USER, 0, None, st)  # fmt: skip
+            rt.ctx.pack([staging.ptr], [out.data_ptr() + done * es], [nb], rt.use_bulk_pack, st)
+        done += n
+    if mean and large:
+        out /= world  # same op the reference applies (`/= N`) on the large-tensor path
+    return out.view(t.shape)
+
+
+def broadcast_(t: torch.Tensor, src: int = 0) -> torch.Tensor:
+    """In place: every rank's ``t`` becomes rank ``src``'s."""
+    rt = SymmRuntime.get()
+    _check_cuda(t, rt, "broadcast")
+    work = t if t.is_contiguous() else t.contiguous()
+    nbytes = work.numel() * work.element_size()
+    if nbytes:
+        staging = rt.ensure_staging()
+        st = _stream()
+        cap = staging.nbytes // 16 * 16
+        done = 0
+        while done < nbytes:
+            n = min(cap, nbytes - done)
+            if rt.rank == src:
+                rt.ctx.pack([work.data_ptr() + done], [staging.ptr], [n], rt.use_bulk_pack, st)
+            rt.ctx.pull(staging.seg, 0, n, work.data_ptr() + done, 0, src, 1, native.CH_USER, 0, st)
+            done += n
+    if work is not t:
+        t.copy_(work)
+    return t
+
+
+def exchange_shape(shape) -> list[list[int]]:
+    """All ranks' shapes as host ints with one tiny kernel (no NCCL, no D2H copy, no stream sync)."""
+    import struct
+
+    rt = SymmRuntime.get()
+    payload = struct.pack(f"<{len(shape)}q", *shape) if len(shape) else b""
+    if len(payload) > native.SMALL_MAX:
+        raise ValueError(f"tensor rank {len(shape)} too large for the shape exchange")
+    if not payload:
+        return [[] for _ in range(rt.world)]
+    parts = rt.ctx.exchange_small(payload, _stream())
+    return [list(struct.unpack(f"<{len(shape)}q", p)) for p in parts]
+
+
+def pad_to_max(t: torch.Tensor, dim: int, pad_index, pad_first: bool) -> torch.Tensor:
+    rt = SymmRuntime.get()
+    _check_cuda(t, rt, "pad_across_processes")
+    sizes = exchange_shape(tuple(t.shape))
+    max_size = max(s[dim] for s in sizes)
+    if max_size == t.shape[dim]:
+        return t
+    # `tensor.new_zeros(..) + pad_index` may promote (int tensor, float pad): follow torch's rule
+    res_dtype = torch.result_type(t, pad_index)
+    src = t if t.dtype == res_dtype else t.to(res_dtype)
+    if not src.is_contiguous():
+        src = src.contiguous()
+    new_shape = list(src.shape)
+    new_shape[dim] = max_size
+    out = torch.empty(new_shape, dtype=src.dtype, device=src.device)
+    es = src.element_size()
+    if es > 8:  # complex128: no native pattern; rare enough to take the 3-op route
+        out = src.new_zeros(new_shape) + pad_index
+        idx = [slice(None)] * len(new_shape)
+        idx[dim] = slice(max_size - src.shape[dim], max_size) if pad_first else slice(0, src.shape[dim])
+        out[tuple(idx)] = src
+        return out
+    pad_bits = int.from_bytes(torch.tensor([pad_index], dtype=src.dtype).view(torch.uint8).numpy().tobytes(), "little")
+    outer = 1
+    for s in src.shape[:dim]:
+        outer *= s
+    inner = 1
+    for s in src.shape[dim + 1 :]:
+        inner *= s
+    rt.ctx.pad_copy(src.data_ptr() if src.numel() else None, out.data_ptr(), outer, src.shape[dim], max_size, inner * es,
+                    es, pad_bits, pad_first, _stream())  # fmt: skip
+    return out

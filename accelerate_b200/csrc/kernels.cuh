@@ -1,0 +1,743 @@
+// kernels.cuh — the sm_100a kernels of the gradient-reduction path.
+//
+//   K1  allreduce_inplace_kernel   fused bucket allreduce (two-shot P2P / NVLS) + pre-divide + stats
+//   K1b allreduce_oneshot_kernel   out-of-place one-shot allreduce for small tensors
+//   K2  pull_kernel                allgather / broadcast by peer loads
+//   K4  pack_kernel / pack_bulk_kernel   multi-tensor bucket pack/unpack (LDG/STG and cp.async.bulk)
+//   K5  multi_stats_kernel / multi_scale_kernel   multi-tensor norm statistics / scaling
+//   K6  finalize_norm_kernel / scale_flat_kernel / clamp_flat_kernel
+//   K7  pad_copy_kernel
+//   K8  exchange_small_kernel
+//
+// All of these are bandwidth-bound (NVLink or HBM); none is a contraction, so no tensor cores.
+#pragma once
+#include "device_utils.cuh"
+
+namespace b200dp {
+
+constexpr int kThreads = 512;        // comm kernels: 1 CTA / SM, 16 warps of 16-byte accesses
+constexpr int kStreamThreads = 256;  // local HBM streaming kernels
+constexpr int kMTMax = 640;          // tensors per multi-tensor launch (table lives in kernel params)
+constexpr int kMTChunk = 8192;       // elements per chunk in multi_stats / multi_scale
+constexpr int kPackChunk = 32768;    // bytes per chunk in pack kernels (= one TMA bulk stage)
+constexpr int kBulkStages = 4;
+
+// ------------------------------------------------------------------------------------------------
+// statistics hand-off: every CTA leaves its partial, the last CTA to arrive folds them in a fixed
+// tree and publishes one Record to slot [slot][rank] of every peer's control segment.
+// ------------------------------------------------------------------------------------------------
+struct StatsSink {
+  Record* partial;    // local scratch [gridDim.x]
+  uint32_t* ticket;   // local arrival counter
+  Peers control;      // control-segment bases (records live at kRecordOff)
+  int slot;           // < 0: no stats
+  int rank, world;    // world == 1 -> publish locally only
+};
+
+__device__ __forceinline__ void publish_stats(const StatsSink& sink, const Stats& mine) {
+  __shared__ uint32_t s_last;
+  double bs;
+  float bm;
+  uint32_t bnf;
+  block_reduce_stats(mine, &bs, &bm, &bnf);
+  if (threadIdx.x == 0) {
+    Record r;
+    r.sumsq = bs;
+    r.maxabs = bm;
+    r.nonfinite = bnf;
+    sink.partial[blockIdx.x] = r;
+    __threadfence();
+    uint32_t t = atomicAdd(sink.ticket, 1u);
+    s_last = (t == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x < 32) {
+    __threadfence();
+    double v = 0.0;
+    float m = 0.f;
+    uint32_t nf = 0;
+    for (int i = threadIdx.x; i < int(gridDim.x); i += 32) {  // fixed assignment -> deterministic
+      const Record* p = sink.partial + i;
+      v += __ldcg(&p->sumsq);
+      m = fmaxf(m, __ldcg(&p->maxabs));
+      nf |= __ldcg(&p->nonfinite);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      v += __shfl_xor_sync(0xffffffffu, v, o);
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      nf |= __shfl_xor_sync(0xffffffffu, nf, o);
+    }
+    if (int(threadIdx.x) < sink.world) {
+      Record* dst = reinterpret_cast<Record*>(reinterpret_cast<char*>(sink.control.p[threadIdx.x]) + kRecordOff) +
+                    (size_t(sink.slot) * B200DP_MAX_WORLD + sink.rank);
+      Record r;
+      r.sumsq = v;
+      r.maxabs = m;
+      r.nonfinite = nf;
+      *dst = r;
+    }
+    if (threadIdx.x == 0) *sink.ticket = 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: in-place fused allreduce of one gradient bucket.
+//   x_i <- sum_r (x_i^(r) * prescale), r ascending, fp32 accumulate, no FMA contraction, so the
+//   result equals the oracle's sequential definition bit for bit (TWOSHOT).  Rank r owns the r-th
+//   1/N of the 16-byte vectors: it loads that slice from all N copies, reduces, and stores the
+//   result into all N copies.  Nobody else touches those addresses, so in place is race-free.
+//   NVLS: the owner issues multimem.ld_reduce (switch adds the N copies) and multimem.st.
+// ------------------------------------------------------------------------------------------------
+struct AllreduceArgs {
+  BarrierCtx bar;
+  Peers bufs;        // segment bases on every rank
+  char* mc;          // multicast VA of the segment (NVLS) or nullptr
+  size_t byte_off;   // bucket start inside the segment (16-byte aligned)
+  size_t nvec;       // 16-byte vectors in the bucket
+  float prescale;
+  StatsSink sink;
+};
+
+template <typename T, int W>
+__device__ __forceinline__ uint4 reduce_vec_twoshot(const AllreduceArgs& a, size_t byte, float prescale, Stats& st,
+                                                    bool want_stats) {
+  constexpr int N = Vec16<T>::N;
+  float acc[N], x[N];
+  if constexpr (W > 0) {
+    uint4 v[W];
+#pragma unroll
+    for (int r = 0; r < W; ++r) v[r] = ld_stream16(reinterpret_cast<const char*>(a.bufs.p[r]) + byte);
+    Vec16<T>::unpack(v[0], acc);
+#pragma unroll
+    for (int k = 0; k < N; ++k) acc[k] = __fmul_rn(acc[k], prescale);
+#pragma unroll
+    for (int r = 1; r < W; ++r) {
+      Vec16<T>::unpack(v[r], x);
+#pragma unroll
+      for (int k = 0; k < N; ++k) acc[k] = __fadd_rn(acc[k], __fmul_rn(x[k], prescale));
+    }
+  } else {  // any world size
+    uint4 v0 = ld_stream16(reinterpret_cast<const char*>(a.bufs.p[0]) + byte);
+    Vec16<T>::unpack(v0, acc);
+#pragma unroll
+    for (int k = 0; k < N; ++k) acc[k] = __fmul_rn(acc[k], prescale);
+    for (int r = 1; r < a.bar.world; ++r) {
+      uint4 v = ld_stream16(reinterpret_cast<const char*>(a.bufs.p[r]) + byte);
+      Vec16<T>::unpack(v, x);
+#pragma unroll
+      for (int k = 0; k < N; ++k) acc[k] = __fadd_rn(acc[k], __fmul_rn(x[k], prescale));
+    }
+  }
+  uint4 out = Vec16<T>::pack(acc);
+  if (want_stats) {
+    Vec16<T>::unpack(out, x);  // stats of the values as stored (after rounding to T)
+#pragma unroll
+    for (int k = 0; k < N; ++k) st.add(x[k]);
+  }
+  return out;
+}
+
+template <typename T, int W, bool NVLS>
+__global__ void __launch_bounds__(kThreads, 1) allreduce_inplace_kernel(const AllreduceArgs a) {
+  const BarrierCtx& b = a.bar;
+  const uint32_t base = barrier_seq_begin(b);
+  const bool want_stats = a.sink.slot >= 0;
+  const int world = b.world;
+
+  // peers' producers (their backward kernels) are stream-ordered before their copy of this kernel
+  cross_rank_barrier(b, base + 1);
+
+  const size_t per_rank = (a.nvec + world - 1) / world;
+  const size_t lo = size_t(b.rank) * per_rank;
+  const size_t hi = (lo + per_rank < a.nvec) ? lo + per_rank : a.nvec;
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  Stats st;
+  constexpr int N = Vec16<T>::N;
+
+  if constexpr (NVLS) {
+    char* mcb = a.mc + a.byte_off;
+    for (size_t i = lo + size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < hi; i += 2 * stride) {
+      const size_t i1 = i + stride;
+      const bool two = i1 < hi;
+      uint4 s0 = MultimemOps<T>::ld_reduce(mcb + i * 16);
+      uint4 s1 = two ? MultimemOps<T>::ld_reduce(mcb + i1 * 16) : make_uint4(0, 0, 0, 0);
+      float f[N];
+      Vec16<T>::unpack(s0, f);
+#pragma unroll
+      for (int k = 0; k < N; ++k) f[k] = __fmul_rn(f[k], a.prescale);
+      uint4 o0 = Vec16<T>::pack(f);
+      if (want_stats) {
+        Vec16<T>::unpack(o0, f);
+#pragma unroll
+        for (int k = 0; k < N; ++k) st.add(f[k]);
+      }
+      multimem_st16(mcb + i * 16, o0);
+      if (two) {
+        Vec16<T>::unpack(s1, f);
+#pragma unroll
+        for (int k = 0; k < N; ++k) f[k] = __fmul_rn(f[k], a.prescale);
+        uint4 o1 = Vec16<T>::pack(f);
+        if (want_stats) {
+          Vec16<T>::unpack(o1, f);
+#pragma unroll
+          for (int k = 0; k < N; ++k) st.add(f[k]);
+        }
+        multimem_st16(mcb + i1 * 16, o1);
+      }
+    }
+  } else {
+    for (size_t i = lo + size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < hi; i += 2 * stride) {
+      const size_t i1 = i + stride;
+      const bool two = i1 < hi;
+      const size_t byte0 = a.byte_off + i * 16, byte1 = a.byte_off + i1 * 16;
+      uint4 o0 = reduce_vec_twoshot<T, W>(a, byte0, a.prescale, st, want_stats);
+      uint4 o1 = make_uint4(0, 0, 0, 0);
+      if (two) o1 = reduce_vec_twoshot<T, W>(a, byte1, a.prescale, st, want_stats);
+      if constexpr (W > 0) {
+#pragma unroll
+        for (int r = 0; r < W; ++r) {
+          st_stream16(reinterpret_cast<char*>(a.bufs.p[r]) + byte0, o0);
+          if (two) st_stream16(reinterpret_cast<char*>(a.bufs.p[r]) + byte1, o1);
+        }
+      } else {
+        for (int r = 0; r < world; ++r) {
+          st_stream16(reinterpret_cast<char*>(a.bufs.p[r]) + byte0, o0);
+          if (two) st_stream16(reinterpret_cast<char*>(a.bufs.p[r]) + byte1, o1);
+        }
+      }
+    }
+  }
+
+  if (want_stats) publish_stats(a.sink, st);
+
+  // all reduced slices (and stats records) have landed everywhere before anyone's kernel retires
+  cross_rank_barrier(b, base + 2);
+  barrier_seq_end(b, base, 2);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1b: out-of-place one-shot allreduce: dst_i = (sum_r staging_r[i]) / divisor.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct ElemTraits {
+  using Acc = T;
+  static __device__ __forceinline__ Acc up(T v) { return v; }
+  static __device__ __forceinline__ T down(Acc v) { return v; }
+  static constexpr bool kFloat = false;
+};
+template <>
+struct ElemTraits<float> {
+  using Acc = float;
+  static __device__ __forceinline__ Acc up(float v) { return v; }
+  static __device__ __forceinline__ float down(Acc v) { return v; }
+  static constexpr bool kFloat = true;
+};
+template <>
+struct ElemTraits<double> {
+  using Acc = double;
+  static __device__ __forceinline__ Acc up(double v) { return v; }
+  static __device__ __forceinline__ double down(Acc v) { return v; }
+  static constexpr bool kFloat = true;
+};
+template <>
+struct ElemTraits<__nv_bfloat16> {
+  using Acc = float;
+  static __device__ __forceinline__ Acc up(__nv_bfloat16 v) { return __bfloat162float(v); }
+  static __device__ __forceinline__ __nv_bfloat16 down(Acc v) { return __float2bfloat16_rn(v); }
+  static constexpr bool kFloat = true;
+};
+template <>
+struct ElemTraits<__half> {
+  using Acc = float;
+  static __device__ __forceinline__ Acc up(__half v) { return __half2float(v); }
+  static __device__ __forceinline__ __half down(Acc v) { return __float2half_rn(v); }
+  static constexpr bool kFloat = true;
+};
+
+struct OneshotArgs {
+  BarrierCtx bar;
+  Peers bufs;
+  size_t byte_off;  // staging offset, 16-byte aligned
+  size_t count;     // elements
+  double divisor;   // 1 = plain sum
+  void* dst;        // local output, 16-byte aligned
+};
+
+template <typename T>
+__device__ __forceinline__ T oneshot_finish(typename ElemTraits<T>::Acc acc, double divisor) {
+  using Tr = ElemTraits<T>;
+  T s = Tr::down(acc);
+  if constexpr (Tr::kFloat) {
+    if (divisor != 1.0) {  // reference: all_reduce(SUM) then `t /= N` in the tensor's own dtype
+      using A = typename Tr::Acc;
+      s = Tr::down(Tr::up(s) / A(divisor));
+    }
+  }
+  return s;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 1) allreduce_oneshot_kernel(const OneshotArgs a) {
+  using Tr = ElemTraits<T>;
+  using Acc = typename Tr::Acc;
+  constexpr int N = 16 / sizeof(T);
+  const BarrierCtx& b = a.bar;
+  const uint32_t base = barrier_seq_begin(b);
+  cross_rank_barrier(b, base + 1);
+
+  const size_t nvec = a.count / N;
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    Acc acc[N];
+    union {
+      uint4 v;
+      T e[N];
+    } u;
+    u.v = ld_stream16(reinterpret_cast<const char*>(a.bufs.p[0]) + a.byte_off + i * 16);
+#pragma unroll
+    for (int k = 0; k < N; ++k) acc[k] = Tr::up(u.e[k]);
+    for (int r = 1; r < b.world; ++r) {
+      u.v = ld_stream16(reinterpret_cast<const char*>(a.bufs.p[r]) + a.byte_off + i * 16);
+#pragma unroll
+      for (int k = 0; k < N; ++k) acc[k] = acc[k] + Tr::up(u.e[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < N; ++k) u.e[k] = oneshot_finish<T>(acc[k], a.divisor);
+    reinterpret_cast<uint4*>(a.dst)[i] = u.v;
+  }
+  if (blockIdx.x == 0) {  // ragged tail, element-wise
+    for (size_t e = nvec * N + threadIdx.x; e < a.count; e += blockDim.x) {
+      Acc acc = Tr::up(reinterpret_cast<const T*>(reinterpret_cast<const char*>(a.bufs.p[0]) + a.byte_off)[e]);
+      for (int r = 1; r < b.world; ++r)
+        acc = acc + Tr::up(reinterpret_cast<const T*>(reinterpret_cast<const char*>(a.bufs.p[r]) + a.byte_off)[e]);
+      reinterpret_cast<T*>(a.dst)[e] = oneshot_finish<T>(acc, a.divisor);
+    }
+  }
+  // nobody may overwrite its staging before every peer has read it
+  cross_rank_barrier(b, base + 2);
+  barrier_seq_end(b, base, 2);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2/K3: pull `nbytes` from peers' staging into local memory (allgather, broadcast).  Bit-exact.
+// ------------------------------------------------------------------------------------------------
+struct PullArgs {
+  BarrierCtx bar;
+  Peers bufs;
+  size_t byte_off;
+  size_t nbytes;
+  char* dst;
+  size_t dst_stride;
+  int first, nranks;
+};
+
+__device__ __forceinline__ void copy_span(char* dst, const char* src, size_t nbytes, size_t tid, size_t nthreads) {
+  // src is always 16-byte aligned (staging); pick the widest unit dst allows
+  const uintptr_t d = reinterpret_cast<uintptr_t>(dst);
+  if ((d & 15) == 0) {
+    const size_t nvec = nbytes >> 4;
+    for (size_t i = tid; i < nvec; i += nthreads)
+      reinterpret_cast<uint4*>(dst)[i] = ld_stream16(src + i * 16);
+    for (size_t i = (nvec << 4) + tid; i < nbytes; i += nthreads) dst[i] = src[i];
+  } else if ((d & 3) == 0) {
+    const size_t nw = nbytes >> 2;
+    for (size_t i = tid; i < nw; i += nthreads)
+      reinterpret_cast<uint32_t*>(dst)[i] = reinterpret_cast<const uint32_t*>(src)[i];
+    for (size_t i = (nw << 2) + tid; i < nbytes; i += nthreads) dst[i] = src[i];
+  } else {
+    for (size_t i = tid; i < nbytes; i += nthreads) dst[i] = src[i];
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) pull_kernel(const PullArgs a) {
+  const BarrierCtx& b = a.bar;
+  const uint32_t base = barrier_seq_begin(b);
+  cross_rank_barrier(b, base + 1);
+  const size_t tid = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t nthreads = size_t(gridDim.x) * blockDim.x;
+  // start with the next rank so that the N readers fan out over N different sources
+  for (int k = 1; k <= b.world; ++k) {
+    const int r = (b.rank + k) % b.world;
+    if (r < a.first || r >= a.first + a.nranks) continue;
+    copy_span(a.dst + size_t(r - a.first) * a.dst_stride, reinterpret_cast<const char*>(a.bufs.p[r]) + a.byte_off,
+              a.nbytes, tid, nthreads);
+  }
+  cross_rank_barrier(b, base + 2);
+  barrier_seq_end(b, base, 2);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: multi-tensor copy (bucket pack / unpack / staging).  One launch for a whole bucket.
+// ------------------------------------------------------------------------------------------------
+struct PackTable {
+  const char* src[kMTMax];
+  char* dst[kMTMax];
+  unsigned long long bytes[kMTMax];
+  uint32_t chunk_start[kMTMax + 1];  // prefix sum of ceil(bytes / kPackChunk)
+  int n;
+};
+
+__device__ __forceinline__ int find_tensor(const uint32_t* chunk_start, int n, uint32_t chunk) {
+  int lo = 0, hi = n;  // last t with chunk_start[t] <= chunk
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (chunk_start[mid] <= chunk) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(kStreamThreads) pack_kernel(const __grid_constant__ PackTable t) {
+  const uint32_t total = t.chunk_start[t.n];
+  for (uint32_t c = blockIdx.x; c < total; c += gridDim.x) {
+    const int ti = find_tensor(t.chunk_start, t.n, c);
+    const size_t off = size_t(c - t.chunk_start[ti]) * kPackChunk;
+    const size_t rem = t.bytes[ti] - off;
+    const size_t n = rem < size_t(kPackChunk) ? rem : size_t(kPackChunk);
+    const char* s = t.src[ti] + off;
+    char* d = t.dst[ti] + off;
+    const uintptr_t al = reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d);
+    if ((al & 15) == 0) {
+      const size_t nvec = n >> 4;
+      for (size_t i = threadIdx.x; i < nvec; i += blockDim.x) st_stream16(d + i * 16, ld_stream16(s + i * 16));
+      for (size_t i = (nvec << 4) + threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];
+    } else if ((al & 3) == 0) {
+      const size_t nw = n >> 2;
+      for (size_t i = threadIdx.x; i < nw; i += blockDim.x)
+        reinterpret_cast<uint32_t*>(d)[i] = reinterpret_cast<const uint32_t*>(s)[i];
+      for (size_t i = (nw << 2) + threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];
+    } else {
+      for (size_t i = threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];
+    }
+  }
+}
+
+// --- TMA-engine variant: one elected thread per CTA drives cp.async.bulk global->smem->global
+// through a ring of kBulkStages x 32 KB stages; the SM's LSU is idle, the copy engine streams.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// All spans must be 16-byte aligned with a size that is a multiple of 16 (the host splits off the rest).
+__global__ void __launch_bounds__(32) pack_bulk_kernel(const __grid_constant__ PackTable t, int* status) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t full[kBulkStages];
+  if (threadIdx.x != 0) return;  // one elected thread; the TMA engine does the work
+  const uint32_t total = t.chunk_start[t.n];
+  for (int s = 0; s < kBulkStages; ++s) mbar_init(&full[s], 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+
+  auto chunk_of = [&](uint32_t j, const char*& s, char*& d, uint32_t& n) {
+    const uint32_t c = blockIdx.x + j * gridDim.x;
+    const int ti = find_tensor(t.chunk_start, t.n, c);
+    const size_t off = size_t(c - t.chunk_start[ti]) * kPackChunk;
+    const size_t rem = t.bytes[ti] - off;
+    n = uint32_t(rem < size_t(kPackChunk) ? rem : size_t(kPackChunk));
+    s = t.src[ti] + off;
+    d = t.dst[ti] + off;
+  };
+  const uint32_t mine = blockIdx.x < total ? (total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  auto issue_load = [&](uint32_t j) {
+    const char* s;
+    char* d;
+    uint32_t n;
+    chunk_of(j, s, d, n);
+    const int st = j % kBulkStages;
+    mbar_expect_tx(&full[st], n);
+    bulk_g2s(smem + size_t(st) * kPackChunk, s, n, &full[st]);
+  };
+  const uint32_t pro = mine < uint32_t(kBulkStages) ? mine : uint32_t(kBulkStages);
+  for (uint32_t j = 0; j < pro; ++j) issue_load(j);
+  for (uint32_t j = 0; j < mine; ++j) {
+    const int st = j % kBulkStages;
+    const uint32_t parity = (j / kBulkStages) & 1;
+    uint32_t spins = 0;
+    while (!mbar_try_wait(&full[st], parity)) {
+      if (++spins > (1u << 26)) {  // ~seconds: never hang the GPU on a lost transaction
+        *reinterpret_cast<volatile int*>(status) = B200DP_ETIMEOUT;
+        return;
+      }
+    }
+    const char* s;
+    char* d;
+    uint32_t n;
+    chunk_of(j, s, d, n);
+    bulk_s2g(d, smem + size_t(st) * kPackChunk, n);
+    bulk_commit();
+    // refill the stage used by chunk j-1 once its store has finished reading shared memory
+    if (j >= 1 && (j - 1) + kBulkStages < mine) {
+      bulk_wait_read<1>();
+      issue_load(j - 1 + kBulkStages);
+    }
+  }
+  bulk_wait_all();
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: multi-tensor statistics / scaling for gradients outside a segment.
+// ------------------------------------------------------------------------------------------------
+struct MTTable {
+  void* ptr[kMTMax];
+  unsigned long long numel[kMTMax];
+  uint32_t chunk_start[kMTMax + 1];  // prefix sum of ceil(numel / kMTChunk)
+  int n;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kStreamThreads) multi_stats_kernel(const __grid_constant__ MTTable t,
+                                                                      const StatsSink sink) {
+  constexpr int N = Vec16<T>::N;
+  const uint32_t total = t.chunk_start[t.n];
+  Stats st;
+  for (uint32_t c = blockIdx.x; c < total; c += gridDim.x) {
+    const int ti = find_tensor(t.chunk_start, t.n, c);
+    const size_t off = size_t(c - t.chunk_start[ti]) * kMTChunk;
+    const size_t rem = t.numel[ti] - off;
+    const size_t n = rem < size_t(kMTChunk) ? rem : size_t(kMTChunk);
+    const T* p = reinterpret_cast<const T*>(t.ptr[ti]) + off;
+    if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+      const size_t nvec = n / N;
+      for (size_t i = threadIdx.x; i < nvec; i += blockDim.x) {
+        float f[N];
+        Vec16<T>::unpack(ld_stream16(reinterpret_cast<const char*>(p) + i * 16), f);
+#pragma unroll
+        for (int k = 0; k < N; ++k) st.add(f[k]);
+      }
+      for (size_t i = nvec * N + threadIdx.x; i < n; i += blockDim.x) st.add(to_float<T>(p[i]));
+    } else {
+      for (size_t i = threadIdx.x; i < n; i += blockDim.x) st.add(to_float<T>(p[i]));
+    }
+  }
+  publish_stats(sink, st);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kStreamThreads) multi_scale_kernel(const __grid_constant__ MTTable t,
+                                                                      const float* __restrict__ mult_ptr) {
+  const float m = *mult_ptr;
+  if (m == 1.0f) return;
+  constexpr int N = Vec16<T>::N;
+  const uint32_t total = t.chunk_start[t.n];
+  for (uint32_t c = blockIdx.x; c < total; c += gridDim.x) {
+    const int ti = find_tensor(t.chunk_start, t.n, c);
+    const size_t off = size_t(c - t.chunk_start[ti]) * kMTChunk;
+    const size_t rem = t.numel[ti] - off;
+    const size_t n = rem < size_t(kMTChunk) ? rem : size_t(kMTChunk);
+    T* p = reinterpret_cast<T*>(t.ptr[ti]) + off;
+    if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+      const size_t nvec = n / N;
+      for (size_t i = threadIdx.x; i < nvec; i += blockDim.x) {
+        float f[N];
+        char* q = reinterpret_cast<char*>(p) + i * 16;
+        Vec16<T>::unpack(ld_stream16(q), f);
+#pragma unroll
+        for (int k = 0; k < N; ++k) f[k] = __fmul_rn(f[k], m);
+        st_stream16(q, Vec16<T>::pack(f));
+      }
+      for (size_t i = nvec * N + threadIdx.x; i < n; i += blockDim.x) p[i] = from_float<T>(to_float<T>(p[i]) * m);
+    } else {
+      for (size_t i = threadIdx.x; i < n; i += blockDim.x) p[i] = from_float<T>(to_float<T>(p[i]) * m);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6: norm finalisation + flat scale / clamp.
+// ------------------------------------------------------------------------------------------------
+// total over records [slot0, slot0+nslots) x ranks; every rank sums the same records in the same
+// order, so total_norm and the multiplier are bit-identical on all ranks.
+__global__ void __launch_bounds__(256) finalize_norm_kernel(const char* control_local, int slot0, int nslots, int r0,
+                                                            int nr, int is_inf_norm, float max_norm,
+                                                            const float* scale_ptr, float* out) {
+  const Record* recs = reinterpret_cast<const Record*>(control_local + kRecordOff);
+  double v = 0.0;
+  float m = 0.f;
+  uint32_t nf = 0;
+  const int total = nslots * nr;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const Record* p = recs + (size_t(slot0 + i / nr) * B200DP_MAX_WORLD + (r0 + i % nr));
+    v += __ldcg(&p->sumsq);
+    m = fmaxf(m, __ldcg(&p->maxabs));
+    nf |= __ldcg(&p->nonfinite);
+  }
+  __shared__ double sh_v[8];
+  __shared__ float sh_m[8];
+  __shared__ uint32_t sh_nf[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    v += __shfl_xor_sync(0xffffffffu, v, o);
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    nf |= __shfl_xor_sync(0xffffffffu, nf, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sh_v[threadIdx.x >> 5] = v;
+    sh_m[threadIdx.x >> 5] = m;
+    sh_nf[threadIdx.x >> 5] = nf;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    v = 0.0;
+    m = 0.f;
+    nf = 0;
+    for (int w = 0; w < 8; ++w) {
+      v += sh_v[w];
+      m = fmaxf(m, sh_m[w]);
+      nf |= sh_nf[w];
+    }
+    float inv_scale = 1.0f;
+    if (scale_ptr != nullptr) inv_scale = float(1.0 / double(*scale_ptr));  // torch: scale.double().reciprocal().float()
+    // 2-norm: inf/NaN inputs propagate through the sum of squares by themselves
+    float total_norm = is_inf_norm ? (nf ? __int_as_float(0x7f800000) : m) : float(sqrt(v));
+    total_norm = total_norm * inv_scale;
+    float mult = inv_scale;
+    if (max_norm >= 0.f) {
+      float coef = max_norm / (total_norm + 1e-6f);  // torch clip_grad_norm_: clamp(max_norm/(total+1e-6), max=1)
+      coef = coef > 1.0f ? 1.0f : coef;              // NaN stays NaN, like torch.clamp
+      mult = inv_scale * coef;
+    }
+    out[0] = total_norm;
+    out[1] = mult;
+    out[2] = nf ? 1.0f : 0.0f;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kStreamThreads) scale_flat_kernel(T* __restrict__ p, size_t count,
+                                                                     const float* __restrict__ mult_ptr) {
+  const float m = *mult_ptr;
+  if (m == 1.0f) return;  // clip inactive: zero HBM traffic
+  constexpr int N = Vec16<T>::N;
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  const size_t tid = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  // head elements up to 16-byte alignment
+  size_t head = 0;
+  const uintptr_t mis = reinterpret_cast<uintptr_t>(p) & 15;
+  if (mis) head = (16 - mis) / sizeof(T);
+  if (head > count) head = count;
+  for (size_t i = tid; i < head; i += stride) p[i] = from_float<T>(to_float<T>(p[i]) * m);
+  char* q = reinterpret_cast<char*>(p + head);
+  const size_t nvec = (count - head) / N;
+  for (size_t i = tid; i < nvec; i += 2 * stride) {
+    const size_t i1 = i + stride;
+    const bool two = i1 < nvec;
+    uint4 a = ld_stream16(q + i * 16);
+    uint4 b = two ? ld_stream16(q + i1 * 16) : make_uint4(0, 0, 0, 0);
+    float f[N];
+    Vec16<T>::unpack(a, f);
+#pragma unroll
+    for (int k = 0; k < N; ++k) f[k] = __fmul_rn(f[k], m);
+    st_stream16(q + i * 16, Vec16<T>::pack(f));
+    if (two) {
+      Vec16<T>::unpack(b, f);
+#pragma unroll
+      for (int k = 0; k < N; ++k) f[k] = __fmul_rn(f[k], m);
+      st_stream16(q + i1 * 16, Vec16<T>::pack(f));
+    }
+  }
+  for (size_t i = head + nvec * N + tid; i < count; i += stride) p[i] = from_float<T>(to_float<T>(p[i]) * m);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kStreamThreads) clamp_flat_kernel(T* __restrict__ p, size_t count, float v) {
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride) {
+    float x = to_float<T>(p[i]);
+    x = x < -v ? -v : (x > v ? v : x);  // NaN passes through, like torch.clamp_
+    p[i] = from_float<T>(x);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7: fused pad copy.  Unit = U bytes (1,2,4,8,16); dst [outer, new_dim, inner_u], src [outer, old_dim, inner_u].
+// ------------------------------------------------------------------------------------------------
+template <typename U>
+__global__ void __launch_bounds__(kStreamThreads) pad_copy_kernel(const U* __restrict__ src, U* __restrict__ dst,
+                                                                   size_t outer, size_t old_dim, size_t new_dim,
+                                                                   size_t inner_u, uint4 pat16, size_t shift) {
+  const size_t total = outer * new_dim * inner_u;
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  const unsigned char* pat = reinterpret_cast<const unsigned char*>(&pat16);
+  for (size_t o = size_t(blockIdx.x) * blockDim.x + threadIdx.x; o < total; o += stride) {
+    const size_t i = o % inner_u;
+    const size_t rest = o / inner_u;
+    const size_t d = rest % new_dim;
+    const size_t ou = rest / new_dim;
+    U val;
+    if (d >= shift && d < shift + old_dim) {
+      val = src[(ou * old_dim + (d - shift)) * inner_u + i];
+    } else {
+      val = *reinterpret_cast<const U*>(pat + ((i * sizeof(U)) & 15));
+    }
+    dst[o] = val;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K8: tiny all-to-all of <=128 bytes per rank, result lands in mapped host memory.
+// ------------------------------------------------------------------------------------------------
+struct SmallPayload {
+  uint32_t w[B200DP_SMALL_MAX / 4];
+};
+__global__ void __launch_bounds__(kThreads, 1) exchange_small_kernel(const BarrierCtx b, const SmallPayload payload,
+                                                                      int nwords, uint32_t* host_out,
+                                                                      volatile int* host_flag, int flag_val) {
+  const uint32_t base = barrier_seq_begin(b);
+  const uint32_t parity = base & 1u;  // exactly one barrier per launch on this channel -> alternates
+  const int t = threadIdx.x;
+  const int n = b.world * nwords;
+  if (t < n) {
+    const int peer = t / nwords, w = t % nwords;
+    uint32_t* slot = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(b.pads.p[peer]) + kSmallOff) +
+                     ((size_t(parity) * B200DP_MAX_WORLD + b.rank) * (B200DP_SMALL_MAX / 4) + w);
+    *slot = payload.w[w];
+  }
+  cross_rank_barrier(b, base + 1);
+  if (t < n) {
+    const int src = t / nwords, w = t % nwords;
+    const uint32_t* slot = reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(b.pads.p[b.rank]) + kSmallOff) +
+                           ((size_t(parity) * B200DP_MAX_WORLD + src) * (B200DP_SMALL_MAX / 4) + w);
+    host_out[src * nwords + w] = __ldcg(slot);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (t == 0) {
+    __threadfence_system();
+    *host_flag = flag_val;
+  }
+  barrier_seq_end(b, base, 1);
+}
+
+}  // namespace b200dp

@@ -1,0 +1,492 @@
+"""B200DataParallel: the gradient reducer that replaces ``torch.nn.parallel.DistributedDataParallel``
+behind ``Accelerator.prepare`` (reference boundary: ``src/accelerate/accelerator.py:1877-1896``).
+
+What torch's DDP + c10d::Reducer + NCCL do per sync-backward:
+
+    per parameter : bucket_view <- grad * (1/N)                    (292 small kernels, GPT-2-medium)
+    per bucket    : ncclAllReduce(SUM) on a side stream             (37 NCCL launches)
+    end of bwd    : grad.copy_(bucket_view)                         (292 small kernels)
+    later         : clip_grad_norm_ = foreach_norm + stack + norm + foreach_mul (reads grads twice)
+
+What this reducer does instead:
+
+* all gradients of one dtype live in ONE symmetric, peer-mapped *fusion buffer*; after the first
+  reduction ``param.grad`` IS a view into it (no copy-back, ever);
+* a gradient that autograd produced elsewhere (fresh ``.grad`` after ``zero_grad(set_to_none=True)``)
+  is moved in by ONE multi-tensor pack launch per bucket (``b200dp_pack``, TMA bulk copies);
+* ONE fused kernel per bucket (``b200dp_allreduce_bucket``) does pre-divide, the allreduce over
+  NVLink by direct peer loads/stores (or NVLS multimem), and accumulates sum-of-squares / max-abs /
+  non-finite statistics of the reduced values, so ``clip_grad_norm_`` and ``GradScaler.unscale_``
+  need no read pass of their own;
+* results are bit-identical on all ranks and equal to ``sum_r fl(g_r * 1/N)`` summed in rank order
+  (the oracle's definition, ``oracle/ddp_oracle.py``; NVLS sums in the switch and scales after,
+  which is the same value whenever N is a power of two).
+
+Semantics mirrored from torch DDP because the reference's tests pin them: the
+decision to reduce is latched at *forward* time from ``require_backward_grad_sync``; ``no_sync()``
+only flips that flag; ``reducer.prepare_for_backward([])`` re-arms; buckets launch in index order;
+parameters are broadcast from rank 0 at wrap time; buffers are re-broadcast each training forward
+when ``broadcast_buffers=True``.
+
+On a CPU device (``DistributedType.MULTI_CPU``, gloo) the same bucket/hook logic runs with
+``torch.distributed.all_reduce`` moving the bytes — that is the reference's own CPU behaviour and
+exists so the host logic is testable without a GPU.  It is selected by the *device type* of the
+module, never as a fallback: a CUDA module without the native library raises.
+"""
+
+from __future__ import annotations
+
+import os
+from contextlib import contextmanager
+
+import torch
+import torch.distributed as dist
+from torch.autograd import Variable
+
+from . import native
+
+import weakref
+
+_ALIGN = 16  # bytes: every parameter slice and bucket starts on a 16-byte boundary
+_LIVE = weakref.WeakSet()
+
+
+def live_reducers():
+    """Reducers currently alive in this process (the GradScaler and clip paths look them up)."""
+    return list(_LIVE)
+
+
+def compute_bucket_assignment(sizes_bytes, keys, first_cap: int, cap: int):
+    """Bucket indices the way ``torch.distributed._compute_bucket_assignment_by_size`` does it.
+
+    Walk tensors in the given order; tensors of one (dtype, device) key fill that key's open
+    bucket; a bucket closes as soon as its bytes reach the key's current limit (``first_cap`` for a
+    key's first bucket, then ``cap``); tensors are never split.  Buckets are returned ordered by
+    their smallest member index.  (``tests/test_reducer_host.py`` checks this against torch.)
+    """
+    open_b: dict = {}
+    limit_idx: dict = {}
+    limits = [first_cap, cap]
+    done = []
+    for i, (nbytes, key) in enumerate(zip(sizes_bytes, keys)):
+        members, total = open_b.get(key, ([], 0))
+        members = members + [i]
+        total += nbytes
+        li = limit_idx.setdefault(key, 0)
+        if total >= limits[li]:
+            done.append(members)
+            open_b[key] = ([], 0)
+            if li + 1 < len(limits):
+                limit_idx[key] = li + 1
+        else:
+            open_b[key] = (members, total)
+    for members, _ in open_b.values():
+        if members:
+            done.append(members)
+    done.sort(key=lambda m: min(m))
+    return done
+
+
+class GradBucket:
+    __slots__ = (
+        "index", "group", "elem_off", "count", "params", "offsets", "numels", "views", "ptrs", "nbytes",
+        "pending", "seen", "staged", "slot", "flat",
+    )  # fmt: skip
+
+    def __init__(self, index, group):
+        self.index, self.group = index, group
+        self.params, self.offsets, self.numels, self.views, self.ptrs, self.nbytes = [], [], [], [], [], []
+        self.elem_off = self.count = 0
+        self.pending = 0
+        self.seen = []
+        self.staged = []
+        self.slot = -1
+        self.flat = None
+
+    def reset(self):
+        self.pending = len(self.params)
+        for i in range(len(self.seen)):
+            self.seen[i] = False
+
+
+class _DtypeGroup:
+    """All gradients of one dtype: one flat fusion buffer (symmetric segment on CUDA)."""
+
+    def __init__(self, dtype):
+        self.dtype = dtype
+        self.elem_size = torch.empty((), dtype=dtype).element_size()
+        self.total_elems = 0
+        self.segment = None  # runtime.Segment (CUDA)
+        self.flat = None  # 1-D tensor over the whole buffer
+        self.native_dtype = None
+
+
+class GradReducer:
+    """Bucket table + autograd hooks + launch ordering.  ``prepare_for_backward`` mirrors the one
+    entry point the reference reaches into (``accelerator.py:1219-1222``)."""
+
+    def __init__(self, owner, params, device, world, rank, bucket_cap_bytes, first_bucket_bytes,
+                 find_unused_parameters, process_group):  # fmt: skip
+        self.owner = owner
+        self.device, self.world, self.rank = device, world, rank
+        self.process_group = process_group
+        self.find_unused_parameters = find_unused_parameters
+        self.is_cuda = device.type == "cuda"
+        self.params = params
+        self._armed = False
+        self._cb_queued = False
+        self._next = 0
+        self.stats_valid = False
+        self.unscaled = False
+        self.wire_dtype = None
+        self.num_reductions = 0  # sync-backwards completed (tests / bench introspection)
+        self.compute_stream = 0
+        self.rt = None
+        if self.is_cuda:
+            from .runtime import SymmRuntime, native_dtype
+
+            self.rt = SymmRuntime.get()  # raises if the native runtime is not up: no fallback
+            self._native_dtype = native_dtype
+            self.comm_stream = self.rt.ctx.comm_stream
+            self.max_blocks = int(os.environ.get("B200DP_REDUCE_BLOCKS", "0"))
+            algo = os.environ.get("B200DP_ALGO", "auto").lower()
+            self.algo = {"auto": native.ALGO_AUTO, "twoshot": native.ALGO_TWOSHOT, "nvls": native.ALGO_NVLS}[algo]
+        for p in params:
+            if p.device != device:
+                raise ValueError(f"parameter on {p.device}, expected {device}: all parameters must sit on the process's device")
+            if p.is_sparse or getattr(p, "layout", torch.strided) != torch.strided:
+                raise ValueError("sparse parameters are not supported by the B200 reducer")
+
+        # ---- bucket table: reverse parameter order ~ gradient-ready order (what DDP starts from) ----
+        order = list(range(len(params)))[::-1]
+        sizes = [params[i].numel() * params[i].element_size() for i in order]
+        keys = [params[i].dtype for i in order]
+        assignment = compute_bucket_assignment(sizes, keys, first_bucket_bytes, bucket_cap_bytes)
+        self.groups: dict = {}
+        self.buckets: list[GradBucket] = []
+        for members in assignment:
+            dtype = keys[members[0]]
+            group = self.groups.setdefault(dtype, _DtypeGroup(dtype))
+            b = GradBucket(len(self.buckets), group)
+            es = group.elem_size
+            align_e = max(1, _ALIGN // es)
+            b.elem_off = group.total_elems
+            cursor = group.total_elems
+            for m in members:
+                p = params[order[m]]
+                b.params.append(p)
+                b.offsets.append(cursor)
+                b.numels.append(p.numel())
+                b.nbytes.append(p.numel() * es)
+                cursor = (cursor + p.numel() + align_e - 1) // align_e * align_e
+            b.count = cursor - b.elem_off
+            group.total_elems = cursor
+            b.seen = [False] * len(b.params)
+            self.buckets.append(b)
+        if len(self.buckets) > 512:
+            raise ValueError(f"{len(self.buckets)} buckets: raise bucket_cap_mb (at most 512 buckets are supported)")
+
+        # ---- fusion buffers ----
+        for group in self.groups.values():
+            nbytes = max(group.total_elems * group.elem_size, _ALIGN)
+            if self.is_cuda:
+                group.native_dtype = self._native_dtype(group.dtype)
+                if group.native_dtype not in (native.F32, native.BF16, native.F16):
+                    raise TypeError(f"gradient dtype {group.dtype} is not supported by the fused allreduce kernel")
+                group.segment = self.rt.alloc_segment(nbytes, multicast=True)
+                group.flat = group.segment.tensor(group.dtype, group.total_elems)
+            else:
+                group.flat = torch.zeros(group.total_elems, dtype=group.dtype, device=device)
+        for b in self.buckets:
+            b.flat = b.group.flat[b.elem_off : b.elem_off + b.count]
+            for p, off, n in zip(b.params, b.offsets, b.numels):
+                v = b.group.flat[off : off + n].view(p.shape)
+                b.views.append(v)
+                b.ptrs.append(v.data_ptr())
+        if self.is_cuda:
+            self.slot_base = self.rt.reserve_slots(len(self.buckets))
+            for b in self.buckets:
+                b.slot = self.slot_base + b.index
+        self._managed_ids = frozenset(id(p) for p in params)
+        self._hooks = []
+        for b in self.buckets:
+            for i, p in enumerate(b.params):
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(b, i)))
+        self._reset_iteration()
+        _LIVE.add(self)
+
+    # ------------------------------------------------------------------ hooks
+    def _make_hook(self, bucket: GradBucket, i: int):
+        ptr, view, seen = bucket.ptrs[i], bucket.views[i], bucket.seen
+
+        def hook(param):
+            if not self._armed:
+                return
+            if not self._cb_queued:
+                self._cb_queued = True
+                Variable._execution_engine.queue_callback(self._finalize_backward)
+            if seen[i]:
+                return  # same parameter fired twice in one backward (retain_graph replays): count once
+            seen[i] = True
+            g = param.grad
+            if g is not None and g.data_ptr() != ptr:
+                # autograd put this gradient somewhere else: adopt it into the fusion buffer
+                bucket.staged.append((i, g if g.is_contiguous() else g.contiguous()))
+                param.grad = view
+            bucket.pending -= 1
+            if bucket.pending == 0:
+                self._launch_ready()
+
+        return hook
+
+    def _launch_ready(self):
+        buckets = self.buckets
+        while self._next < len(buckets) and buckets[self._next].pending == 0:  # strictly in index order
+            self._reduce_bucket(buckets[self._next])
+            self._next += 1
+
+    # ------------------------------------------------------------------ the data path
+    def _reduce_bucket(self, b: GradBucket):
+        if self.is_cuda:
+            ctx = self.rt.ctx
+            cs = self.compute_stream
+            if b.staged:
+                srcs = [g.data_ptr() for _, g in b.staged]
+                dsts = [b.ptrs[i] for i, _ in b.staged]
+                sizes = [b.nbytes[i] for i, _ in b.staged]
+                ctx.pack(srcs, dsts, sizes, self.rt.use_bulk_pack, cs)
+                b.staged.clear()  # the pack is stream-ordered before any reuse of that memory
+            seg = b.group.segment
+            algo = self.algo
+            if algo == native.ALGO_AUTO:
+                algo = native.ALGO_NVLS if (seg.multicast and self.world > 1) else native.ALGO_TWOSHOT
+            ctx.allreduce_bucket(seg.seg, b.elem_off, b.count, b.group.native_dtype, 1.0 / self.world, b.slot,
+                                 native.F_STATS, algo, native.CH_GRAD, self.max_blocks, cs, self.comm_stream)  # fmt: skip
+        else:
+            for i, g in b.staged:
+                b.views[i].copy_(g)
+            b.staged.clear()
+            # same arithmetic as DDP: pre-divide, then SUM (reducer.hpp:276,524)
+            b.flat.mul_(1.0 / self.world)
+            if self.world > 1:
+                dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.process_group)
+
+    def _finalize_backward(self):
+        """Autograd-engine callback: runs once, after the last gradient of this backward."""
+        try:
+            if self._next < len(self.buckets):
+                self._handle_unready()
+            if self.is_cuda:
+                # the optimizer (compute stream) must see the reduced gradients
+                self.rt.ctx.stream_wait(self.compute_stream, self.comm_stream)
+                self.stats_valid = True
+                self.unscaled = False
+            self.num_reductions += 1
+        finally:
+            self._armed = False
+            self._reset_iteration()
+
+    def _handle_unready(self):
+        missing = [(b, i) for b in self.buckets[self._next :] for i in range(len(b.params)) if not b.seen[i]]
+        if missing and not self.find_unused_parameters:
+            names = {id(p): n for n, p in self.owner.module.named_parameters()}
+            some = ", ".join(names.get(id(b.params[i]), "?") for b, i in missing[:8])
+            raise RuntimeError(
+                f"{len(missing)} parameter(s) did not receive a gradient in this backward pass (e.g. {some}). "
+                "Wrap with DistributedDataParallelKwargs(find_unused_parameters=True) if parts of the model are "
+                "conditionally unused."
+            )
+        for b, i in missing:
+            b.views[i].zero_()  # contributes 0 to the mean; the slice may hold last step's values
+            b.params[i].grad = b.views[i]
+            b.seen[i] = True
+            b.pending -= 1
+        self._launch_ready()
+
+    def _reset_iteration(self):
+        self._next = 0
+        self._cb_queued = False
+        for b in self.buckets:
+            b.reset()
+
+    # ------------------------------------------------------------------ API the wrapper / Accelerator use
+    def prepare_for_backward(self, unused=None):
+        """Arm the next backward (torch Reducer::prepare_for_backward; reached from accelerator.py:1222)."""
+        self._armed = True
+        self.stats_valid = False
+        if self.is_cuda:
+            self.compute_stream = torch.cuda.current_stream(self.device).cuda_stream
+        self._reset_iteration()
+
+    def grads_in_buffer(self) -> bool:
+        """Every managed parameter's ``.grad`` is (still) its view into the fusion buffer."""
+        for b in self.buckets:
+            for p, ptr in zip(b.params, b.ptrs):
+                g = p.grad
+                if g is None or g.data_ptr() != ptr:
+                    return False
+        return True
+
+    def manages(self, parameters) -> bool:
+        """True iff ``parameters`` (those with grads) are exactly this reducer's parameters and their
+        gradients live in its buffers — the precondition for using the fused statistics."""
+        ids = {id(p) for p in parameters if p.grad is not None}
+        return ids == self._managed_ids and self.grads_in_buffer()
+
+    def fused_clip_(self, max_norm: float, norm_type: float = 2.0, scale: torch.Tensor | None = None):
+        """clip_grad_norm_ and/or GradScaler.unscale_ from the statistics the allreduce kernels already
+        produced: one 1-CTA finalize + one multiply pass over the fusion buffer that exits at once
+        when the multiplier is 1.  Returns a 3-float device tensor ``[total_norm, multiplier,
+        found_inf]``.
+
+        * ``scale=None``: plain clip (bf16 / fp32 runs).
+        * ``scale=S, max_norm<0``: unscale only (``g *= 1/S``); statistics stay usable for a later clip.
+        * ``scale=S, max_norm>=0``: unscale and clip in one pass — or, if an unscale already ran, clip
+          only (the norm is still derived from the scaled statistics: ``total = total_scaled / S``).
+        """
+        if not (self.is_cuda and self.stats_valid):
+            raise RuntimeError("fused_clip_ needs fresh reduction statistics (call right after a sync backward)")
+        ctx = self.rt.ctx
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        out = torch.empty(3, dtype=torch.float32, device=self.device)
+        scale_ptr = scale.data_ptr() if scale is not None else None
+        ctx.finalize_norm(self.slot_base, len(self.buckets), True, norm_type, max_norm, scale_ptr, out.data_ptr(), st)
+        if scale is not None and self.unscaled:
+            # gradients already carry 1/S: keep only the clip coefficient (exact for power-of-two S)
+            out[1].mul_(scale.to(torch.float32).reshape(()))
+        mult_ptr = out.data_ptr() + 4
+        for group in self.groups.values():
+            ctx.scale_flat(group.flat.data_ptr(), group.total_elems, group.native_dtype, mult_ptr, 0, st)
+        if scale is not None:
+            self.unscaled = True
+        if max_norm >= 0:
+            self.stats_valid = False  # the buffer no longer holds the values the statistics describe
+        return out
+
+    def clamp_(self, clip_value: float):
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        for group in self.groups.values():
+            self.rt.ctx.clamp_flat(group.flat.data_ptr(), group.total_elems, group.native_dtype, clip_value, 0, st)
+        self.stats_valid = False
+
+    def broadcast_parameters(self, module_params):
+        """Make every rank's parameters equal rank 0's through the fusion buffers: pack, pull, unpack."""
+        if self.world == 1:
+            return
+        if not self.is_cuda:
+            for p in module_params:
+                dist.broadcast(p.data, src=0, group=self.process_group)
+            return
+        ctx = self.rt.ctx
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.no_grad():
+            for group in self.groups.values():
+                mine = [(p, ptr, nb) for b in self.buckets if b.group is group for p, ptr, nb in zip(b.params, b.ptrs, b.nbytes)]
+                if self.rank == 0:
+                    ctx.pack([p.data_ptr() for p, _, _ in mine], [ptr for _, ptr, _ in mine], [nb for _, _, nb in mine],
+                             self.rt.use_bulk_pack, st)  # fmt: skip
+                nbytes = group.total_elems * group.elem_size
+                ctx.pull(group.segment.seg, 0, nbytes, group.flat.data_ptr(), 0, 0, 1, native.CH_USER, 0, st)
+                for p, _, _ in mine:
+                    if not p.is_contiguous():
+                        raise ValueError("non-contiguous parameters are not supported by the B200 reducer")
+                ctx.pack([ptr for _, ptr, _ in mine], [p.data_ptr() for p, _, _ in mine], [nb for _, _, nb in mine],
+                         self.rt.use_bulk_pack, st)  # fmt: skip
+                group.flat.zero_()
+
+    def remove_hooks(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+
+
+class B200DataParallel(torch.nn.Module):
+    """Drop-in for the ``DistributedDataParallel(model, device_ids=[local_rank], output_device=local_rank,
+    **DistributedDataParallelKwargs.to_kwargs())`` call at ``accelerator.py:1892-1894``; exposes the
+    attributes the reference and its tests read."""
+
+    def __init__(self, module, device_ids=None, output_device=None, dim=0, broadcast_buffers=True,
+                 process_group=None, bucket_cap_mb=None, find_unused_parameters=False, check_reduction=False,
+                 gradient_as_bucket_view=False, static_graph=False):  # fmt: skip
+        super().__init__()
+        params = [p for p in module.parameters() if p.requires_grad]
+        if not params:
+            raise RuntimeError("B200DataParallel is not needed when a module doesn't have any parameter that requires a gradient.")
+        self.module = module
+        device = params[0].device
+        self.device_ids = [torch.device(d).index if not isinstance(d, int) else d for d in device_ids] if device_ids else None
+        self.output_device = output_device
+        self.dim = dim
+        self.broadcast_buffers = broadcast_buffers
+        self.find_unused_parameters = find_unused_parameters
+        self.gradient_as_bucket_view = gradient_as_bucket_view
+        self.static_graph = static_graph
+        self.process_group = process_group
+        self.require_backward_grad_sync = True
+        self.require_forward_param_sync = True
+        world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        rank = dist.get_rank(process_group) if dist.is_initialized() else 0
+        # torch: bucket_cap_mb=None -> 25 MiB cap and a 1 MiB first bucket; explicit value -> both equal
+        if bucket_cap_mb is None:
+            self.bucket_bytes_cap_default = True
+            self.bucket_bytes_cap = 25 * 1024 * 1024
+            first = 1024 * 1024
+        else:
+            self.bucket_bytes_cap_default = False
+            self.bucket_bytes_cap = int(bucket_cap_mb * 1024 * 1024)
+            first = self.bucket_bytes_cap
+        self.reducer = GradReducer(self, params, device, world, rank, self.bucket_bytes_cap, first,
+                                   find_unused_parameters, process_group)  # fmt: skip
+        # rank 0's weights (and buffers) become everyone's (torch: _sync_module_states)
+        self.reducer.broadcast_parameters(params)
+        self._sync_buffers()
+
+    # ---- DDP surface ----
+    @contextmanager
+    def no_sync(self):
+        previous = self.require_backward_grad_sync
+        self.require_backward_grad_sync = False
+        try:
+            yield
+        finally:
+            self.require_backward_grad_sync = previous
+
+    def register_comm_hook(self, state, hook):
+        from .utils.dataclasses import DDPCommunicationHookType
+
+        if isinstance(hook, DDPCommunicationHookType):
+            raise NotImplementedError(
+                f"comm hook {hook}: the half-precision wire format is not implemented yet (SURVEY.md §8f row 3)"
+            )
+        raise NotImplementedError(
+            "arbitrary Python communication hooks are not supported: the allreduce is a fused device kernel"
+        )
+
+    def _sync_buffers(self):
+        bufs = [b for b in self.module.buffers() if b is not None]
+        if not bufs or self.reducer.world == 1:
+            return
+        from .utils.operations import broadcast
+
+        with torch.no_grad():
+            broadcast(bufs, from_process=0)
+
+    def forward(self, *inputs, **kwargs):
+        if self.device_ids:  # torch DDP moves inputs to its device (_pre_forward -> _to_kwargs)
+            from .utils.operations import send_to_device
+
+            dev = torch.device(self.reducer.device.type, self.device_ids[0])
+            inputs = send_to_device(inputs, dev)
+            kwargs = send_to_device(kwargs, dev)
+        if self.broadcast_buffers and self.require_forward_param_sync and self.training:
+            self._sync_buffers()
+        if torch.is_grad_enabled() and self.require_backward_grad_sync:
+            self.reducer.prepare_for_backward([])  # latched at forward time, as in torch
+        else:
+            self.reducer._armed = False
+        return self.module(*inputs, **kwargs)
+
+
+def find_reducers(model_or_models):
+    models = model_or_models if isinstance(model_or_models, (list, tuple)) else [model_or_models]
+    return [m.reducer for m in models if isinstance(m, B200DataParallel)]

@@ -1,0 +1,204 @@
+"""Configuration surface of the data-parallel path: the plugin boundary.
+
+Same class names, field names, defaults and ``to_kwargs()`` (diff-from-default) behaviour as the
+reference's ``src/accelerate/utils/dataclasses.py`` for the handlers the hot path consumes:
+``DistributedDataParallelKwargs`` (:154-237), ``DDPCommunicationHookType`` (:134-151),
+``GradScalerKwargs`` (:240-269), ``AutocastKwargs`` (:112-131), ``InitProcessGroupKwargs``
+(:272-299), ``GradientAccumulationPlugin`` (:976-1025), ``DataLoaderConfiguration`` (:818-910),
+``DistributedType`` (:600-636), ``PrecisionType`` (:769-782).  Other backends' plugins (FSDP,
+DeepSpeed, Megatron, TP/CP/SP, FP8 recipes) are out of scope for this build.
+"""
+
+from __future__ import annotations
+
+import copy
+import dataclasses
+import enum
+import os
+import warnings
+from dataclasses import dataclass, field
+from datetime import timedelta
+from typing import Any, Callable, Optional
+
+
+class KwargsHandler:
+    """Mixin for config dataclasses: ``to_kwargs()`` returns only the fields that differ from a default instance."""
+
+    def to_dict(self) -> dict:
+        return copy.deepcopy(self.__dict__)
+
+    def to_kwargs(self) -> dict:
+        from .environment import clear_environment
+
+        with clear_environment():  # defaults must not depend on the caller's env
+            baseline = type(self)().to_dict()
+        mine = self.to_dict()
+        return {name: value for name, value in mine.items() if baseline[name] != value}
+
+
+class _ContainsMeta(enum.EnumMeta):
+    def __contains__(cls, item):
+        try:
+            cls(item)
+            return True
+        except ValueError:
+            return False
+
+
+class BaseEnum(enum.Enum, metaclass=_ContainsMeta):
+    def __str__(self):
+        return self.value
+
+    @classmethod
+    def list(cls):
+        return [str(m) for m in cls]
+
+
+class DistributedType(str, enum.Enum):
+    """Only the values this build can take: no distributed run, multi-GPU (CUDA) and multi-CPU (gloo; host-logic tests)."""
+
+    NO = "NO"
+    MULTI_CPU = "MULTI_CPU"
+    MULTI_GPU = "MULTI_GPU"
+
+
+class PrecisionType(str, BaseEnum):
+    NO = "no"
+    FP16 = "fp16"
+    BF16 = "bf16"
+    FP8 = "fp8"  # recognised so that the error message is helpful; not supported by this build
+
+
+class RNGType(BaseEnum):
+    TORCH = "torch"
+    CUDA = "cuda"
+    GENERATOR = "generator"
+
+
+class GradientSyncMode(BaseEnum):
+    """How clip_grad_norm_ consumed the reduction statistics (introspection / tests)."""
+
+    FUSED = "fused"
+    MULTI_TENSOR = "multi_tensor"
+
+
+@dataclass
+class AutocastKwargs(KwargsHandler):
+    enabled: bool = True
+    cache_enabled: Optional[bool] = None
+
+
+class DDPCommunicationHookType(BaseEnum):
+    NO = "no"
+    FP16 = "fp16"
+    BF16 = "bf16"
+    POWER_SGD = "power_sgd"
+    BATCHED_POWER_SGD = "batched_power_sgd"
+
+
+@dataclass
+class DistributedDataParallelKwargs(KwargsHandler):
+    """Knobs of the gradient reducer; field-compatible with the reference (dataclasses.py:181-195).
+
+    ``comm_hook`` FP16/BF16 select a half-precision *wire* format inside the fused allreduce (the
+    reference's compress hooks, dataclasses.py:206-216); PowerSGD variants are not implemented.
+    """
+
+    dim: int = 0
+    broadcast_buffers: bool = True
+    bucket_cap_mb: int = 25
+    find_unused_parameters: bool = False
+    check_reduction: bool = False
+    gradient_as_bucket_view: bool = False
+    static_graph: bool = False
+
+    comm_hook: DDPCommunicationHookType = DDPCommunicationHookType.NO
+    comm_wrapper: DDPCommunicationHookType = DDPCommunicationHookType.NO
+    comm_state_option: dict = field(default_factory=dict)
+
+    def to_dict(self, ignore_keys=("comm_hook", "comm_wrapper", "comm_state_option")):
+        return {k: v for k, v in super().to_dict().items() if k not in ignore_keys}
+
+    def register_comm_hook(self, model):
+        """Mirror of dataclasses.py:200-237: translate the enum into a hook on the wrapper."""
+        hook, wrapper = self.comm_hook, self.comm_wrapper
+        if hook == DDPCommunicationHookType.NO and wrapper == DDPCommunicationHookType.NO:
+            return
+        if DDPCommunicationHookType.POWER_SGD in (hook, wrapper) or DDPCommunicationHookType.BATCHED_POWER_SGD in (
+            hook,
+            wrapper,
+        ):
+            raise NotImplementedError("PowerSGD communication hooks are not implemented by the B200 reducer")
+        wire = hook if hook != DDPCommunicationHookType.NO else wrapper
+        model.register_comm_hook(dict(self.comm_state_option), wire)
+
+
+@dataclass
+class GradScalerKwargs(KwargsHandler):
+    init_scale: float = 65536.0
+    growth_factor: float = 2.0
+    backoff_factor: float = 0.5
+    growth_interval: int = 2000
+    enabled: bool = True
+
+
+@dataclass
+class InitProcessGroupKwargs(KwargsHandler):
+    backend: Optional[str] = "nccl"
+    init_method: Optional[str] = None
+    timeout: Optional[timedelta] = None
+
+    def __post_init__(self):
+        if self.timeout is None:
+            seconds = 1800 if self.backend != "nccl" else 600
+            self.timeout = timedelta(seconds=seconds)
+
+
+@dataclass
+class GradientAccumulationPlugin(KwargsHandler):
+    num_steps: int = None
+    adjust_scheduler: bool = True
+    sync_with_dataloader: bool = True
+    sync_each_batch: bool = False
+
+
+@dataclass
+class DataLoaderConfiguration:
+    split_batches: bool = False
+    dispatch_batches: Optional[bool] = None
+    even_batches: bool = True
+    use_seedable_sampler: bool = False
+    data_seed: Optional[int] = None
+    non_blocking: bool = False
+    use_stateful_dataloader: bool = False
+
+    def __post_init__(self):
+        if self.use_stateful_dataloader:
+            raise NotImplementedError("torchdata StatefulDataLoader is not supported by this build")
+
+
+@dataclass
+class ProjectConfiguration:
+    project_dir: Optional[str] = None
+    logging_dir: Optional[str] = None
+    automatic_checkpoint_naming: bool = False
+    total_limit: Optional[int] = None
+    iteration: int = 0
+    save_on_each_node: bool = False
+
+    def set_directories(self, project_dir: Optional[str] = None):
+        self.project_dir = project_dir
+        if self.logging_dir is None:
+            self.logging_dir = project_dir
+
+    def __post_init__(self):
+        self.set_directories(self.project_dir)
+
+
+@dataclass
+class TensorInformation:
+    shape: Any
+    dtype: Any
+
+
+__all__ = [n for n, v in list(globals().items()) if isinstance(v, type) and v.__module__ == __name__]
