@@ -1,0 +1,45 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests", "golden")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
+
+
+@pytest.fixture(autouse=True)
+def _fresh_state():
+    """Every test starts with pristine Borg singletons (the reference's AccelerateTestCase.tearDown)."""
+    yield
+    from accelerate_b200.state import AcceleratorState, GradientState
+
+    AcceleratorState._reset_state()
+    GradientState._reset_state()
+    # PartialState (process group / native runtime) survives: one per test process
+
+
+def run_distributed(script, nproc, *args, env=None, timeout=600):
+    """torchrun a script under tests/scripts with `nproc` ranks on this node; returns combined output."""
+    import socket
+    import subprocess
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port),
+           os.path.join(ROOT, "tests", "scripts", script), *args]  # fmt: skip
+    full_env = dict(os.environ)
+    full_env.setdefault("OMP_NUM_THREADS", "1")
+    full_env.update(env or {})
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=full_env, cwd=ROOT)
+    out = res.stdout + "\n" + res.stderr
+    assert res.returncode == 0, f"{' '.join(cmd)} failed ({res.returncode}):\n{out[-6000:]}"
+    return out

@@ -1,0 +1,189 @@
+"""Multi-rank parity check of accelerate_b200 against the reference's golden fixtures and the oracle.
+
+Launched by the tests with torchrun (``--device cpu``: gloo, host logic; ``--device cuda``: the P2P
+kernels — on a 1-GPU box all ranks share the GPU, which the kernels support by time-slicing).
+Prints ``DIST_CHECK_OK`` on success, raises otherwise.
+"""
+
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+
+from scenarios import make_batch, make_model, ops_inputs  # noqa: E402
+
+from oracle import ddp_oracle as oracle  # noqa: E402  (tests may import the oracle)
+
+RTOL, ATOL = 1e-3, 1e-5  # BASELINE.json: gradient parity tolerance vs the reference DDP path
+
+
+def npy(t):
+    return t.detach().float().cpu().numpy() if t.dtype == torch.bfloat16 else t.detach().cpu().numpy()
+
+
+def same_bits(a, b):
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    return a.shape == b.shape and a.dtype == b.dtype and a.tobytes() == b.tobytes()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--device", default="cpu")
+    args = ap.parse_args()
+    cpu = args.device == "cpu"
+    if cpu:
+        os.environ["ACCELERATE_USE_CPU"] = "yes"
+        torch.set_num_threads(1)
+
+    from accelerate_b200 import Accelerator, B200DataParallel
+    from accelerate_b200.state import AcceleratorState, GradientState, PartialState
+    from accelerate_b200.utils import broadcast
+
+    acc = Accelerator(cpu=cpu)
+    rank, world, dev = acc.process_index, acc.num_processes, acc.device
+    assert world in (2, 4), world
+    gold_ops = np.load(os.path.join(ROOT, "tests", "golden", f"ops_w{world}.npz"))
+    exact_sum = world == 2  # one commutative add: every summation order gives the same bits
+
+    # ------------------------------------------------------------ collectives vs the reference's outputs
+    for name, t in ops_inputs(rank, world).items():
+        t = t.to(dev)
+        got = npy(acc.gather(t.clone()))
+        assert same_bits(got, gold_ops[f"r{rank}/gather/{name}"]), f"gather/{name} differs from the reference"
+        if t.dtype != torch.bool:
+            got = npy(acc.reduce(t.clone(), "sum"))
+            ref = gold_ops[f"r{rank}/reduce_sum/{name}"]
+            ok = same_bits(got, ref) if (exact_sum or not t.is_floating_point()) else np.allclose(got, ref, RTOL, ATOL)
+            assert ok, f"reduce_sum/{name}: {got} vs {ref}"
+            if t.is_floating_point():
+                got = npy(acc.reduce(t.clone(), "mean"))
+                ref = gold_ops[f"r{rank}/reduce_mean/{name}"]
+                ok = same_bits(got, ref) if exact_sum else np.allclose(got, ref, RTOL, ATOL)
+                assert ok, f"reduce_mean/{name}: {got} vs {ref}"
+            before = t.clone()
+            acc.reduce(t, "sum")
+            assert torch.equal(before, t), "reduce must not mutate its input"
+        b = t.clone()
+        ret = broadcast(b, from_process=world - 1)
+        assert ret is b, "broadcast returns the same tensor object"
+        assert same_bits(npy(b), gold_ops[f"r{rank}/broadcast/{name}"]), f"broadcast/{name}"
+    ragged = (torch.arange((rank + 2) * 3, dtype=torch.float32).reshape(rank + 2, 3) + 100 * rank).to(dev)
+    assert same_bits(npy(acc.pad_across_processes(ragged, dim=0)), gold_ops[f"r{rank}/pad/dim0"])
+    assert same_bits(npy(acc.pad_across_processes(ragged, dim=0, pad_index=-1, pad_first=True)), gold_ops[f"r{rank}/pad/dim0_first"])
+    ragged1 = (torch.arange(2 * (rank + 1), dtype=torch.int64).reshape(2, rank + 1) + 10 * rank).to(dev)
+    assert same_bits(npy(acc.pad_across_processes(ragged1, dim=1, pad_index=7)), gold_ops[f"r{rank}/pad/dim1"])
+    assert same_bits(npy(acc.pad_across_processes(ragged1, dim=-1, pad_index=7, pad_first=True)), gold_ops[f"r{rank}/pad/dimneg"])
+    full = torch.ones(3, 2, device=dev)
+    assert acc.pad_across_processes(full, dim=0) is full, "already-max tensors come back as the same object"
+    assert acc.pad_across_processes(full, dim=5) is full
+    # oracle agrees with the reference on the same inputs (sanity of the checker itself)
+    per_rank = [ops_inputs(r, world)["f32"].numpy() for r in range(world)]
+    assert same_bits(oracle.gather(per_rank), gold_ops[f"r{rank}/gather/f32"])
+
+    # ------------------------------------------------------------ DDP gradient path
+    for precision, tag in (("no", "fp32"), ("bf16", "bf16")):
+        gold = np.load(os.path.join(ROOT, "tests", "golden", f"ddp_w{world}_{tag}.npz"))
+        AcceleratorState._reset_state()
+        GradientState._reset_state()
+        acc = Accelerator(cpu=cpu, mixed_precision=precision)
+        model = acc.prepare(make_model())
+        assert isinstance(model, B200DataParallel)
+        local = make_model().to(dev)
+        x, y = (t.to(dev) for t in make_batch(rank, 0))
+        with acc.autocast():
+            torch.nn.functional.mse_loss(local(x), y).backward()
+        loss = torch.nn.functional.mse_loss(model(x), y)
+        acc.backward(loss)
+        params = list(model.parameters())
+        for i, (p, lp) in enumerate(zip(params, local.parameters())):
+            assert p.grad.dtype == torch.float32  # grads stay fp32 under autocast
+            got = npy(p.grad)
+            ref = gold[f"r{rank}/ddp/{i}"]
+            if cpu and tag == "fp32":
+                assert same_bits(npy(lp.grad), gold[f"r{rank}/local/{i}"]), "local grad differs: scenario drifted"
+            if cpu and (exact_sum or True):
+                # same arithmetic, same gloo ring as the reference's DDP on CPU
+                assert np.allclose(got, ref, RTOL, ATOL), f"{tag} ddp grad {i}"
+                if exact_sum:
+                    assert same_bits(got, ref), f"{tag} ddp grad {i}: not bit-identical to reference DDP at N=2"
+            else:
+                assert np.allclose(got, ref, RTOL, ATOL), f"{tag} ddp grad {i} vs reference beyond rtol/atol"
+            # against the oracle on THIS run's local gradients: bit-exact, any N (rank-order sum)
+            locals_all = npy(acc.gather(lp.grad.reshape(1, -1)))
+            want = oracle.ddp_mean_reduce([locals_all[r] for r in range(world)]).reshape(got.shape)
+            if not cpu or exact_sum:
+                assert same_bits(got, want), f"{tag} grad {i}: differs from oracle sum_r fl(g_r/N)"
+            # identical on every rank
+            everyone = npy(acc.gather(p.grad.reshape(1, -1)))
+            assert all(same_bits(everyone[0], everyone[r]) for r in range(world)), "ranks disagree"
+        tn = acc.clip_grad_norm_(model.parameters(), 0.05)
+        assert acc.last_clip_mode == ("torch" if cpu else "fused"), acc.last_clip_mode
+        assert np.allclose(tn.item(), gold[f"r{rank}/clip/total_norm"], RTOL, ATOL), (tn.item(), gold[f"r{rank}/clip/total_norm"])
+        for i, p in enumerate(params):
+            assert np.allclose(npy(p.grad), gold[f"r{rank}/clip/{i}"], RTOL, ATOL), f"{tag} clipped grad {i}"
+        model.zero_grad()
+
+        # ---- accumulation: micro-step 0 must NOT communicate, micro-step 1 reduces the accumulated grads
+        AcceleratorState._reset_state()
+        GradientState._reset_state()
+        acc = Accelerator(cpu=cpu, mixed_precision=precision, gradient_accumulation_steps=2)
+        model2 = acc.prepare(make_model())
+        for micro in range(2):
+            x, y = (t.to(dev) for t in make_batch(rank, 1 + micro))
+            with acc.accumulate(model2):
+                acc.backward(torch.nn.functional.mse_loss(model2(x), y))
+            assert int(acc.sync_gradients) == int(gold[f"r{rank}/accum/sync_flag/{micro}"])
+            if micro == 0:
+                assert model2.reducer.num_reductions == 0, "no_sync micro-step communicated"
+                for i, p in enumerate(model2.parameters()):
+                    assert np.allclose(npy(p.grad), gold[f"r{rank}/accum/micro0/{i}"], RTOL, ATOL)
+        assert model2.reducer.num_reductions == 1
+        for i, p in enumerate(model2.parameters()):
+            assert np.allclose(npy(p.grad), gold[f"r{rank}/accum/ddp/{i}"], RTOL, ATOL), f"{tag} accum grad {i}"
+
+    # ------------------------------------------------------------ sync latched at forward time
+    AcceleratorState._reset_state()
+    GradientState._reset_state()
+    acc = Accelerator(cpu=cpu)
+    model = acc.prepare(make_model())
+    x, y = (t.to(dev) for t in make_batch(rank, 5))
+    with acc.no_sync(model):
+        out = model(x)
+    torch.nn.functional.mse_loss(out, y).backward()  # backward outside no_sync: still no reduction
+    assert model.reducer.num_reductions == 0
+    with acc.no_sync(model):
+        out = model(x)
+    with acc.trigger_sync_in_backward(model):
+        torch.nn.functional.mse_loss(out, y).backward()
+    assert model.reducer.num_reductions == 1
+    everyone = npy(acc.gather(next(model.parameters()).grad.reshape(1, -1)))
+    assert all(same_bits(everyone[0], everyone[r]) for r in range(world))
+    # parameters were broadcast from rank 0 at wrap time
+    torch.manual_seed(100 + rank)
+    odd = torch.nn.Linear(8, 8).to(dev)
+    wrapped = acc.prepare(odd)
+    w = npy(acc.gather(wrapped.module.weight.detach().reshape(1, -1)))
+    assert all(same_bits(w[0], w[r]) for r in range(world)), "wrap must broadcast rank 0's parameters"
+    assert acc.unwrap_model(wrapped) is odd
+    # check_trigger: a flag raised on one rank is seen by all
+    if rank == world - 1:
+        acc.set_trigger()
+    assert acc.check_trigger() is True
+    assert acc.check_trigger() is False
+
+    if not cpu:
+        PartialState().runtime.ctx.check_status()
+        torch.cuda.synchronize()
+    acc.wait_for_everyone()
+    print(f"DIST_CHECK_OK rank {rank}/{world} device {dev}", flush=True)
+    PartialState().destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,29 @@
+"""-m gpu: multi-rank parity of the P2P kernels through the public API, against the reference's golden
+outputs and the oracle.  With fewer GPUs than ranks the ranks share a GPU (PartialState picks gloo for
+the rendezvous group, the data path is unchanged)."""
+
+import pytest
+import torch
+
+from conftest import run_distributed
+
+pytestmark = pytest.mark.gpu
+
+ENV = {"B200DP_TIMEOUT_MS": "60000"}
+
+
+@pytest.mark.parametrize("kind", ["fd", "ipc"])
+def test_two_ranks_against_golden(kind):
+    out = run_distributed("dist_check.py", 2, "--device", "cuda", env={**ENV, "B200DP_SEG_KIND": kind}, timeout=900)
+    assert out.count("DIST_CHECK_OK") == 2, out[-3000:]
+
+
+def test_four_ranks_against_golden():
+    out = run_distributed("dist_check.py", 4, "--device", "cuda", env=ENV, timeout=1200)
+    assert out.count("DIST_CHECK_OK") == 4, out[-3000:]
+
+
+def test_gpt2_small_grads_two_ranks():
+    """BASELINE.json config 2 shape: GPT-2-small-like block stack, fp32, 2 ranks, grads vs oracle + torch DDP semantics."""
+    out = run_distributed("dist_gpt2.py", 2, env=ENV, timeout=1200)
+    assert out.count("GPT2_CHECK_OK") == 2, out[-3000:]
