@@ -1,0 +1,13 @@
+"""World-size-2 and -4 runs on CPU (gloo): the N>1 host path — bucket table, autograd hooks, forward-time
+sync latch, accumulate/no_sync, trigger_sync_in_backward, parameter broadcast, collectives — checked
+against the golden outputs of the reference (tests/scripts/dist_check.py)."""
+
+import pytest
+
+from conftest import run_distributed
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_dist_check_cpu(world):
+    out = run_distributed("dist_check.py", world, "--device", "cpu", timeout=600)
+    assert out.count("DIST_CHECK_OK") == world, out[-3000:]
