@@ -49,6 +49,10 @@ import weakref
 
 _ALIGN = 16  # bytes: every parameter slice and bucket starts on a 16-byte boundary
 _LIVE = weakref.WeakSet()
+# debugging switches (diagnostics only; defaults are the product configuration)
+_DEBUG = os.environ.get("B200DP_DEBUG", "0") == "1"
+_KEEP_STAGED = os.environ.get("B200DP_KEEP_STAGED", "0") == "1"
+_SAME_STREAM = os.environ.get("B200DP_SAME_STREAM", "0") == "1"
 
 
 def live_reducers():
@@ -141,6 +145,7 @@ class GradReducer:
         self.wire_dtype = None
         self.num_reductions = 0  # sync-backwards completed (tests / bench introspection)
         self.compute_stream = 0
+        self._graveyard = []
         self.rt = None
         if self.is_cuda:
             from .runtime import SymmRuntime, native_dtype
@@ -255,13 +260,19 @@ class GradReducer:
                 dsts = [b.ptrs[i] for i, _ in b.staged]
                 sizes = [b.nbytes[i] for i, _ in b.staged]
                 ctx.pack(srcs, dsts, sizes, self.rt.use_bulk_pack, cs)
+                if _DEBUG:
+                    print(f"[b200dp r{self.rank}] bucket {b.index}: pack {len(srcs)} spans on stream {cs:#x}: "
+                          f"{[(hex(s_), hex(d_), n_) for s_, d_, n_ in zip(srcs, dsts, sizes)]}", flush=True)
+                if _KEEP_STAGED:
+                    self._graveyard.extend(g for _, g in b.staged)
                 b.staged.clear()  # the pack is stream-ordered before any reuse of that memory
             seg = b.group.segment
             algo = self.algo
             if algo == native.ALGO_AUTO:
                 algo = native.ALGO_NVLS if (seg.multicast and self.world > 1) else native.ALGO_TWOSHOT
+            comm = cs if _SAME_STREAM else self.comm_stream
             ctx.allreduce_bucket(seg.seg, b.elem_off, b.count, b.group.native_dtype, 1.0 / self.world, b.slot,
-                                 native.F_STATS, algo, native.CH_GRAD, self.max_blocks, cs, self.comm_stream)  # fmt: skip
+                                 native.F_STATS, algo, native.CH_GRAD, self.max_blocks, cs, comm)  # fmt: skip
         else:
             for i, g in b.staged:
                 b.views[i].copy_(g)
@@ -278,7 +289,9 @@ class GradReducer:
                 self._handle_unready()
             if self.is_cuda:
                 # the optimizer (compute stream) must see the reduced gradients
-                self.rt.ctx.stream_wait(self.compute_stream, self.comm_stream)
+                if not _SAME_STREAM:
+                    self.rt.ctx.stream_wait(self.compute_stream, self.comm_stream)
+                self._graveyard.clear()
                 self.stats_valid = True
                 self.unscaled = False
             self.num_reductions += 1

@@ -1,0 +1,176 @@
+"""-m gpu: the public API on one GPU — clip paths, gradients-as-views life cycle, fp16 loss scaling with
+the fused unscale/clip (reference pins: tests/test_optimizer.py:40-82 overflow => skipped step), unused
+parameters.  World size 1 exercises the full reducer (pack -> fused allreduce+stats -> clip) when the
+wrapper is constructed by hand."""
+
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def mlp(seed=0, dtype=torch.float32):
+    torch.manual_seed(seed)
+    return torch.nn.Sequential(torch.nn.Linear(64, 257), torch.nn.GELU(), torch.nn.Linear(257, 33)).cuda().to(dtype)
+
+
+def torch_clip_reference(grads, max_norm, norm_type=2.0):
+    params = [torch.nn.Parameter(torch.empty(0, device=g.device)) for g in grads]
+    for p, g in zip(params, grads):
+        p.grad = g.clone()
+    tn = torch.nn.utils.clip_grad_norm_(params, max_norm, norm_type=norm_type)
+    return tn, [p.grad for p in params]
+
+
+@pytest.mark.parametrize("norm_type", [2.0, math.inf])
+def test_multi_tensor_clip_matches_torch(norm_type):
+    from accelerate_b200 import Accelerator
+
+    acc = Accelerator()
+    model = acc.prepare(mlp())
+    x = torch.randn(16, 64, device="cuda")
+    acc.backward(model(x).square().mean() * 100)
+    grads = [p.grad.clone() for p in model.parameters()]
+    ref_tn, ref = torch_clip_reference(grads, 0.5, norm_type)
+    tn = acc.clip_grad_norm_(model.parameters(), 0.5, norm_type)
+    assert acc.last_clip_mode == "multi_tensor"
+    assert torch.allclose(tn, ref_tn, rtol=1e-5)
+    for p, r in zip(model.parameters(), ref):
+        assert torch.allclose(p.grad, r, rtol=1e-5, atol=1e-9)
+    # subset of parameters + no clipping needed (coef clamps to 1: grads untouched, bit for bit)
+    sub = list(model.parameters())[:2]
+    before = [p.grad.clone() for p in sub]
+    tn2 = acc.clip_grad_norm_(sub, 1e9)
+    assert all(torch.equal(p.grad, b) for p, b in zip(sub, before))
+    assert torch.allclose(tn2, torch_clip_reference(before, 1e9)[0], rtol=1e-5)
+
+
+def test_gradients_become_views_and_are_repacked():
+    from accelerate_b200 import Accelerator, B200DataParallel
+    from accelerate_b200.state import PartialState
+
+    acc = Accelerator()
+    model = mlp()
+    ddp = B200DataParallel(model, device_ids=[0], bucket_cap_mb=0.05)  # several buckets
+    assert len(ddp.reducer.buckets) >= 2 and ddp.bucket_bytes_cap == int(0.05 * 2**20)
+    opt = acc.prepare(torch.optim.SGD(model.parameters(), lr=0.1))
+    rt = PartialState().runtime
+    x = torch.randn(8, 64, device="cuda")
+    flat = next(iter(ddp.reducer.groups.values())).flat
+
+    def step(set_to_none):
+        ddp(x).square().mean().backward()
+        for b in ddp.reducer.buckets:
+            for p, ptr in zip(b.params, b.ptrs):
+                assert p.grad.data_ptr() == ptr, "grad must live in the fusion buffer after a sync backward"
+        ref_tn, ref = torch_clip_reference([p.grad for p in model.parameters()], 0.01)
+        tn = acc.clip_grad_norm_(ddp.parameters(), 0.01)
+        assert acc.last_clip_mode == "fused"
+        assert torch.allclose(tn, ref_tn, rtol=1e-5)
+        for p, r in zip(model.parameters(), ref):
+            assert torch.allclose(p.grad, r, rtol=1e-5, atol=1e-10)
+        opt.step()
+        opt.zero_grad(set_to_none=set_to_none)
+
+    step(True)
+    assert all(p.grad is None for p in model.parameters())
+    launches = rt.ctx.launches
+    step(False)  # fresh grads -> one pack per bucket + one allreduce per bucket + finalize + scale
+    nb = len(ddp.reducer.buckets)
+    assert rt.ctx.launches - launches >= 2 * nb + 2
+    assert all(p.grad is not None and p.grad.abs().sum() == 0 for p in model.parameters())
+    launches = rt.ctx.launches
+    step(False)  # grads are already views: autograd accumulates in place, NO pack launches
+    assert rt.ctx.launches - launches == nb + 2, "no pack expected when grads already live in the fusion buffer"
+    assert ddp.reducer.num_reductions == 3
+    # second backward without a forward in between must not reduce again (expect_autograd_hooks semantics)
+    out = ddp(x).square().mean()
+    out.backward(retain_graph=True)
+    n = ddp.reducer.num_reductions
+    out.backward()
+    assert ddp.reducer.num_reductions == n
+    # clip_grad_value_ on the fusion buffer
+    acc.clip_grad_value_(ddp.parameters(), 1e-4)
+    assert all(p.grad.abs().max() <= 1e-4 for p in model.parameters())
+    assert flat.abs().max() <= 1e-4
+    rt.ctx.check_status()
+
+
+def test_unused_parameters():
+    from accelerate_b200 import B200DataParallel
+    from accelerate_b200.state import PartialState
+
+    PartialState()
+
+    class TwoHeads(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a = torch.nn.Linear(8, 8)
+            self.b = torch.nn.Linear(8, 8)
+
+        def forward(self, x, use_b):
+            return self.b(x) if use_b else self.a(x)
+
+    x = torch.randn(4, 8, device="cuda")
+    strict = B200DataParallel(TwoHeads().cuda(), device_ids=[0])
+    with pytest.raises(RuntimeError, match="did not receive a gradient"):
+        strict(x, False).sum().backward()
+    strict.reducer.remove_hooks()
+    lenient = B200DataParallel(TwoHeads().cuda(), device_ids=[0], find_unused_parameters=True)
+    lenient(x, False).sum().backward()
+    assert lenient.module.b.weight.grad is not None and lenient.module.b.weight.grad.abs().sum() == 0
+    assert lenient.module.a.weight.grad.abs().sum() > 0
+
+
+def test_fp16_scaler_fused_unscale_clip_and_overflow_skip():
+    from accelerate_b200 import Accelerator, B200DataParallel, GradScalerKwargs
+
+    acc = Accelerator(mixed_precision="fp16", kwargs_handlers=[GradScalerKwargs(init_scale=1024.0, growth_interval=1)])
+    model = mlp()
+    ddp = B200DataParallel(model, device_ids=[0])
+    opt = acc.prepare(torch.optim.SGD(model.parameters(), lr=0.01))
+    x = torch.randn(8, 64, device="cuda")
+    with acc.autocast():
+        loss = ddp(x).float().square().mean()
+    acc.backward(loss)
+    scaled = [p.grad.clone() for p in model.parameters()]
+    ref_tn, ref = torch_clip_reference([g / 1024.0 for g in scaled], 0.05)
+    tn = acc.clip_grad_norm_(ddp.parameters(), 0.05)  # ONE pass: unscale and clip
+    assert acc.last_clip_mode == "fused"
+    assert torch.allclose(tn, ref_tn, rtol=1e-5)
+    for p, r in zip(model.parameters(), ref):
+        assert torch.allclose(p.grad, r, rtol=1e-5, atol=1e-10)
+    before = [p.detach().clone() for p in model.parameters()]
+    opt.step()
+    assert not opt.step_was_skipped and acc.scaler.get_scale() == 2048.0  # growth_interval=1
+    assert any(not torch.equal(b, p) for b, p in zip(before, model.parameters()))
+    opt.zero_grad()
+
+    # overflow: a non-finite gradient on the wire -> found_inf from the allreduce statistics -> step skipped
+    with acc.autocast():
+        loss = ddp(x).float().square().mean() * float("inf")
+    acc.backward(loss)
+    before = [p.detach().clone() for p in model.parameters()]
+    opt.step()  # scaler.step -> unscale_ (fused override) -> found_inf -> no optimizer.step
+    assert opt.step_was_skipped and acc.optimizer_step_was_skipped
+    assert all(torch.equal(b, p) for b, p in zip(before, model.parameters()))
+    assert acc.scaler.get_scale() == 1024.0  # backoff 0.5
+    opt.zero_grad()
+
+    # separate unscale_gradients() then clip: norm still comes from the (scaled) statistics
+    with acc.autocast():
+        loss = ddp(x).float().square().mean()
+    acc.backward(loss)
+    scaled = [p.grad.clone() for p in model.parameters()]
+    acc.unscale_gradients()
+    for p, g in zip(model.parameters(), scaled):
+        assert torch.equal(p.grad, g * (1.0 / 1024.0))
+    ref_tn, ref = torch_clip_reference([g / 1024.0 for g in scaled], 0.05)
+    tn = acc.clip_grad_norm_(ddp.parameters(), 0.05)
+    assert acc.last_clip_mode == "fused" and torch.allclose(tn, ref_tn, rtol=1e-5)
+    for p, r in zip(model.parameters(), ref):
+        assert torch.allclose(p.grad, r, rtol=1e-5, atol=1e-10)
+    opt.step()
+    assert not opt.step_was_skipped

@@ -94,12 +94,12 @@ def test_finalize_and_scale_match_torch_clip(rt):
         p = torch.nn.Parameter(x.clone())
         p.grad = x.clone()
         tn = torch.nn.utils.clip_grad_norm_([p], 1.0)
-        assert abs(res[0] - tn.item()) <= 1e-6 * tn.item()
         want_clipped, want_tn = oracle.clip_grad_norm([x.numpy()], 1.0)
-        assert abs(res[0] - want_tn) <= 1e-6 * want_tn
+        assert abs(res[0] - want_tn) <= 1e-6 * want_tn  # oracle accumulates in float64
+        assert abs(res[0] - tn.item()) <= 2e-4 * tn.item()  # torch CPU sums 3M squares in float32
         # given the device's multiplier the scaling itself is bit-exact
         assert np.array_equal(v.cpu().numpy(), x.numpy() * np.float32(res[1]))
-        assert np.allclose(v.cpu().numpy(), p.grad.numpy(), rtol=1e-6, atol=0)
+        assert np.allclose(v.cpu().numpy(), p.grad.numpy(), rtol=2e-4, atol=0)
         # multiplier 1 -> untouched bits, no traffic
         one = torch.ones(1, device=rt.device)
         before = v.clone()
