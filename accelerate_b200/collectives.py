@@ -97,7 +97,7 @@ def all_reduce(t: torch.Tensor, mean: bool = False) -> torch.Tensor:
             # two-shot / NVLS in place on the staging copy, then one copy out
             padded = (nb + 15) // 16 * 16 // es
             rt.ctx.allreduce_bucket(staging.seg, 0, padded, dt, 1.0, -1, 0, native.ALGO_AUTO if staging.multicast
-                                    else native.ALGO_TWOSHOT, native.CH_USER, 0, None, st)  # fmt: skip
+                                    else native.ALGO_TWOSHOT, native.CH_USER, 0, native.NO_STREAM, st)  # fmt: skip
             rt.ctx.pack([staging.ptr], [out.data_ptr() + done * es], [nb], rt.use_bulk_pack, st)
         done += n
     if mean and large:

@@ -745,7 +745,7 @@ extern "C" int b200dp_allreduce_bucket(b200dp_ctx* c, int seg, size_t elem_off, 
   const size_t per_rank = (a.nvec + c->world - 1) / c->world;
   const int grid = clamp_blocks(c, per_rank, size_t(kThreads) * 2, max_blocks);
   cudaStream_t st = (cudaStream_t)stream;
-  if (after_stream != nullptr && after_stream != stream) {
+  if (after_stream != B200DP_NO_STREAM && after_stream != stream) {
     if ((rc = b200dp_stream_wait(c, stream, after_stream))) return rc;
   }
   switch (dtype) {

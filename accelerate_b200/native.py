@@ -34,6 +34,7 @@ ALGO_AUTO, ALGO_TWOSHOT, ALGO_NVLS, ALGO_ONESHOT = 0, 1, 2, 3
 F_STATS = 1
 Q_LAUNCHES, Q_MULTICAST_OK, Q_VMM_OK, Q_STATUS, Q_SM_COUNT, Q_COMM_STREAM = range(6)
 ETIMEOUT = -4
+NO_STREAM = ctypes.c_void_p(-1).value  # B200DP_NO_STREAM: stream 0 is a real stream, so NULL cannot mean 'none'
 
 EXPORTS = [
     "b200dp_version", "b200dp_last_error", "b200dp_init", "b200dp_finalize", "b200dp_query",

@@ -134,9 +134,10 @@ def cpu_leg(model_name, steps, warmup, budget_s=25.0, micro_batch=1):
     import psutil
     import torch
 
-    from oracle import ddp_oracle as oracle
+    from oracle import c_oracle
 
     cores = psutil.cpu_count(logical=False) or os.cpu_count()
+    os.environ.setdefault("ORACLE_THREADS", str(cores))
     torch.set_num_threads(cores)
     model = build_model(model_name)
     model.train()
@@ -151,9 +152,7 @@ def cpu_leg(model_name, steps, warmup, budget_s=25.0, micro_batch=1):
             loss = model(input_ids=ids, labels=ids).loss
         loss.backward()
         params = [p for p in model.parameters() if p.grad is not None]
-        clipped, _ = oracle.clip_grad_norm([p.grad.numpy() for p in params], 1.0)
-        for p, c in zip(params, clipped):
-            p.grad.copy_(torch.from_numpy(np.ascontiguousarray(c)))
+        c_oracle.clip_grad_norm_inplace([p.grad.numpy() for p in params], 1.0)  # in place on the grads' memory
         opt.step()
         opt.zero_grad()
         dt = time.perf_counter() - t0
@@ -164,7 +163,7 @@ def cpu_leg(model_name, steps, warmup, budget_s=25.0, micro_batch=1):
     mean = sum(times) / len(times)
     return {"value": micro_batch / mean, "unit": "samples/s", "cores": cores, "kind": "port",
             "sample": f"{len(times)} steps x {micro_batch} sequence(s) of {SEQ} tokens, {model_name}, torch CPU bf16 autocast "
-                      f"fwd/bwd + oracle clip_grad_norm + AdamW; {mean * 1e3:.0f} ms/step"}  # fmt: skip
+                      f"fwd/bwd + oracle (C, pthreads) clip_grad_norm + AdamW; {mean * 1e3:.0f} ms/step"}  # fmt: skip
 
 
 def run_reference_arm(args):
@@ -296,7 +295,7 @@ def main():
                             "+ clip_grad_norm_(1.0) + AdamW + zero_grad",
                 "global_batch": gb, "per_gpu_batch": B, "seq_len": SEQ, "parallelism": f"dp{world}", "bucket_cap_mb": 25,
                 "l2": "per-step working set (1.4 GB grads + weights + activations) exceeds the 126 MB L2; no flush needed",
-                "clip_mode": clip_mode, "final_loss": float(last_loss),
+                "clip_mode": clip_mode, "final_loss": float(last_loss.detach()),
             },
             "e2e": {"value": gb * steps / (e2e_ms / 1e3), "unit": "samples/s", "h2d_bytes_per_step": B * SEQ * 8,
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / steps},
@@ -372,11 +371,11 @@ def kernel_roofline(acc, model, rt, world, peaks, peak_src):
         acc.wait_for_everyone()
         for _ in range(3):
             rt.ctx.allreduce_bucket(group.segment.seg, 0, cnt, native.F32, 1.0 / world, red.slot_base, native.F_STATS,
-                                    algo, native.CH_GRAD, 0, None, st)  # fmt: skip
+                                    algo, native.CH_GRAD, 0, native.NO_STREAM, st)  # fmt: skip
         for i in range(reps):
             ev[2 * i].record()
             rt.ctx.allreduce_bucket(group.segment.seg, 0, cnt, native.F32, 1.0 / world, red.slot_base, native.F_STATS,
-                                    algo, native.CH_GRAD, 0, None, st)  # fmt: skip
+                                    algo, native.CH_GRAD, 0, native.NO_STREAM, st)  # fmt: skip
             ev[2 * i + 1].record()
         torch.cuda.synchronize()
         t = torch.tensor([sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(reps)) / reps], device=dev)

@@ -70,7 +70,7 @@ def main():
         for name, algo in algos:
             for blocks in blocks_list:
                 ms = timeit(lambda: rt.ctx.allreduce_bucket(seg.seg, 0, n, native.F32, 1.0 / world, 0, native.F_STATS, algo,
-                                                            native.CH_USER, blocks, None, st), nbytes)  # fmt: skip
+                                                            native.CH_USER, blocks, native.NO_STREAM, st), nbytes)  # fmt: skip
                 row[f"{name}_b{blocks}_us"] = ms * 1e3
                 row[f"{name}_b{blocks}_busbw"] = nbytes * 2 * (world - 1) / world / (ms * 1e-3) / 1e9
             flat[:n].normal_()  # keep values bounded: the in-place mean keeps shrinking them otherwise

@@ -68,6 +68,10 @@ extern "C" {
 #define B200DP_ALGO_NVLS 2    /* multimem.ld_reduce + multimem.st on the multicast mapping */
 #define B200DP_ALGO_ONESHOT 3 /* out-of-place only: every rank loads all N copies */
 
+/* "no stream" sentinel for optional stream arguments.  NULL cannot be used: cudaStream_t 0 is the
+ * (legacy) default stream, which is a perfectly valid stream to order after. */
+#define B200DP_NO_STREAM ((void*)(intptr_t)-1)
+
 /* flags for b200dp_allreduce_bucket */
 #define B200DP_F_STATS 1 /* accumulate sum-of-squares / max-abs / non-finite into the slot record */
 
@@ -137,7 +141,8 @@ int b200dp_stream_wait(b200dp_ctx* ctx, void* waiter, void* signaller);
  * In place on segment `seg`, elements [elem_off, elem_off+count) of type dtype:
  *   x_i <- sum_{r=0..N-1} ( x_i^{(r)} * prescale )   in rank order, fp32 accumulation,
  * identical bits on every rank.  Stats of the reduced values go to record `slot`.
- * If after_stream != NULL the launch is ordered after everything already on after_stream. */
+ * If after_stream != B200DP_NO_STREAM the launch is ordered after everything already enqueued on
+ * after_stream (event record + wait; after_stream may be 0 = the default stream). */
 int b200dp_allreduce_bucket(b200dp_ctx* ctx, int seg, size_t elem_off, size_t count, int dtype,
                             float prescale, int slot, int flags, int algo, int channel,
                             int max_blocks, void* after_stream, void* stream);

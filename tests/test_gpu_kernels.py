@@ -54,7 +54,7 @@ def test_allreduce_bucket_world1_and_stats(rt, dtype, numel):
         slot = rt.reserve_slots(1)
         es = x.element_size()
         rt.ctx.allreduce_bucket(seg.seg, 16 // es, numel, DT[dtype], 0.25, slot, native.F_STATS, native.ALGO_TWOSHOT,
-                                native.CH_GRAD, 0, None, stream())
+                                native.CH_GRAD, 0, native.NO_STREAM, stream())
         out = torch.empty(3, device=rt.device)
         rt.ctx.finalize_norm(slot, 1, True, 2.0, -1.0, None, out.data_ptr(), stream())
         got = view.float().cpu()
@@ -67,7 +67,7 @@ def test_allreduce_bucket_world1_and_stats(rt, dtype, numel):
         # inf-norm + found_inf
         view[numel // 2] = float("inf")
         rt.ctx.allreduce_bucket(seg.seg, 16 // es, numel, DT[dtype], 1.0, slot, native.F_STATS, native.ALGO_TWOSHOT,
-                                native.CH_GRAD, 0, None, stream())
+                                native.CH_GRAD, 0, native.NO_STREAM, stream())
         rt.ctx.finalize_norm(slot, 1, True, math.inf, -1.0, None, out.data_ptr(), stream())
         res = read_out(out)
         assert res[2] == 1.0 and math.isinf(res[0])
@@ -86,7 +86,7 @@ def test_finalize_and_scale_match_torch_clip(rt):
         v = seg.tensor(torch.float32, n)
         v.copy_(x)
         slot = rt.reserve_slots(1)
-        rt.ctx.allreduce_bucket(seg.seg, 0, n, 0, 1.0, slot, native.F_STATS, native.ALGO_TWOSHOT, native.CH_GRAD, 0, None, stream())
+        rt.ctx.allreduce_bucket(seg.seg, 0, n, 0, 1.0, slot, native.F_STATS, native.ALGO_TWOSHOT, native.CH_GRAD, 0, native.NO_STREAM, stream())
         out = torch.empty(3, device=rt.device)
         rt.ctx.finalize_norm(slot, 1, True, 2.0, 1.0, None, out.data_ptr(), stream())
         rt.ctx.scale_flat(v.data_ptr(), n, 0, out.data_ptr() + 4, 0, stream())
@@ -264,7 +264,7 @@ def test_full_size_properties(rt):
         ref_sumsq = float((v.double() ** 2).sum())
         ref_sum = float(v.double().sum())
         slot = rt.reserve_slots(1)
-        rt.ctx.allreduce_bucket(seg.seg, 0, n, 0, 0.5, slot, native.F_STATS, native.ALGO_TWOSHOT, native.CH_GRAD, 0, None, stream())
+        rt.ctx.allreduce_bucket(seg.seg, 0, n, 0, 0.5, slot, native.F_STATS, native.ALGO_TWOSHOT, native.CH_GRAD, 0, native.NO_STREAM, stream())
         out = torch.empty(3, device=rt.device)
         rt.ctx.finalize_norm(slot, 1, True, 2.0, 1.0, None, out.data_ptr(), stream())
         res = read_out(out)
