@@ -382,6 +382,22 @@ def kernel_roofline(acc, model, rt, world, peaks, peak_src):
         t = acc.gather(t).max().item()
         bus = (cnt * 4) * 2 * (world - 1) / world / (t * 1e-3) / 1e9
         sizes[label] = {"bytes": cnt * 4, "ms": t, "busbw_GBps": bus, "algbw_GBps": cnt * 4 / (t * 1e-3) / 1e9}
+    # bucket pack (what replaces DDP's per-parameter copy-in): TMA bulk vs LDG/STG, on a mid-size real bucket
+    mid = sorted(red.buckets, key=lambda bk: bk.count)[len(red.buckets) // 2]
+    fresh = [torch.randn_like(p) for p in mid.params]
+    pack = {"bucket_bytes": sum(mid.nbytes), "tensors": len(mid.params)}
+    for label, bulk in (("bulk_tma", 1), ("ldg_stg", 0)):
+        srcs, dsts = [f.data_ptr() for f in fresh], list(mid.ptrs)
+        for _ in range(3):
+            rt.ctx.pack(srcs, dsts, mid.nbytes, bulk, st)
+        for i in range(reps):
+            ev[2 * i].record()
+            rt.ctx.pack(srcs, dsts, mid.nbytes, bulk, st)
+            ev[2 * i + 1].record()
+        torch.cuda.synchronize()
+        t = sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(reps)) / reps
+        pack[label] = {"ms": t, "GBps": 2 * sum(mid.nbytes) / (t * 1e-3) / 1e9}
+    extra["pack_kernel"] = pack
     group.flat.zero_()
     b = sizes["bucket_25MiB"]
     roof = {"kernel": f"allreduce_inplace_kernel<float,{'NVLS' if algo == native.ALGO_NVLS else 'twoshot'}>", "bound": "nvlink",

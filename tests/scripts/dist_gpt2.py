@@ -22,7 +22,7 @@ def build(seed=42, layers=12):
     from transformers import GPT2Config, GPT2LMHeadModel
 
     torch.manual_seed(seed)
-    cfg = GPT2Config(n_layer=layers, resid_pdrop=0.0, embd_pdrop=0.0, attn_pdrop=0.0)
+    cfg = GPT2Config(n_layer=layers, resid_pdrop=0.0, embd_pdrop=0.0, attn_pdrop=0.0, attn_implementation="eager")  # eager attention: deterministic backward
     return GPT2LMHeadModel(cfg)
 
 
@@ -60,7 +60,7 @@ def main():
     ref_grads = [p.grad.detach().clone() for p in model.parameters()]
     tn = acc.clip_grad_norm_(model.parameters(), 1.0)
     assert acc.last_clip_mode == "fused"
-    ref_params = [torch.nn.Parameter(torch.empty(0, device=dev)) for _ in ref_grads]
+    ref_params = [torch.nn.Parameter(torch.empty_like(g_)) for g_ in ref_grads]
     for rp, rg in zip(ref_params, ref_grads):
         rp.grad = rg
     ref_tn = torch.nn.utils.clip_grad_norm_(ref_params, 1.0)

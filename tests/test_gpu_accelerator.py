@@ -17,7 +17,7 @@ def mlp(seed=0, dtype=torch.float32):
 
 
 def torch_clip_reference(grads, max_norm, norm_type=2.0):
-    params = [torch.nn.Parameter(torch.empty(0, device=g.device)) for g in grads]
+    params = [torch.nn.Parameter(torch.empty_like(g)) for g in grads]
     for p, g in zip(params, grads):
         p.grad = g.clone()
     tn = torch.nn.utils.clip_grad_norm_(params, max_norm, norm_type=norm_type)
@@ -53,8 +53,8 @@ def test_gradients_become_views_and_are_repacked():
 
     acc = Accelerator()
     model = mlp()
-    ddp = B200DataParallel(model, device_ids=[0], bucket_cap_mb=0.05)  # several buckets
-    assert len(ddp.reducer.buckets) >= 2 and ddp.bucket_bytes_cap == int(0.05 * 2**20)
+    ddp = B200DataParallel(model, device_ids=[0], bucket_cap_mb=0.02)  # several buckets
+    assert len(ddp.reducer.buckets) >= 2 and ddp.bucket_bytes_cap == int(0.02 * 2**20)
     opt = acc.prepare(torch.optim.SGD(model.parameters(), lr=0.1))
     rt = PartialState().runtime
     x = torch.randn(8, 64, device="cuda")
@@ -159,7 +159,9 @@ def test_fp16_scaler_fused_unscale_clip_and_overflow_skip():
     assert acc.scaler.get_scale() == 1024.0  # backoff 0.5
     opt.zero_grad()
 
-    # separate unscale_gradients() then clip: norm still comes from the (scaled) statistics
+    # explicit unscale_gradients() (no clip): one multiply pass by 1/scale, found_inf from the statistics.
+    # (Calling clip_grad_norm_ afterwards would raise in the reference too: GradScaler.unscale_ may run
+    # only once per step, accelerator.py:2944/3007.)
     with acc.autocast():
         loss = ddp(x).float().square().mean()
     acc.backward(loss)
@@ -167,10 +169,7 @@ def test_fp16_scaler_fused_unscale_clip_and_overflow_skip():
     acc.unscale_gradients()
     for p, g in zip(model.parameters(), scaled):
         assert torch.equal(p.grad, g * (1.0 / 1024.0))
-    ref_tn, ref = torch_clip_reference([g / 1024.0 for g in scaled], 0.05)
-    tn = acc.clip_grad_norm_(ddp.parameters(), 0.05)
-    assert acc.last_clip_mode == "fused" and torch.allclose(tn, ref_tn, rtol=1e-5)
-    for p, r in zip(model.parameters(), ref):
-        assert torch.allclose(p.grad, r, rtol=1e-5, atol=1e-10)
+    with pytest.raises(RuntimeError, match="already been called"):
+        acc.clip_grad_norm_(ddp.parameters(), 0.05)
     opt.step()
     assert not opt.step_was_skipped
