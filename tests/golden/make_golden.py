@@ -147,6 +147,34 @@ def _worker(rank, world, port, outdir):
             res[f"accum/ddp/{i}"] = p.grad.numpy().copy()
         tag = "fp32" if precision == "no" else "bf16"
         np.savez(os.path.join(outdir, f"ddp_{tag}_r{rank}.npz"), **res)
+    # ---- prepared dataloaders: per-rank batches, end-of-epoch flags, gather_for_metrics truncation ----
+    from scenarios import LOADER_GRID, loader_dataset
+
+    loaders = []
+    for length, bs, drop_last, split, dispatch, iterable in LOADER_GRID:
+        if split and bs % world:
+            continue
+        AcceleratorState._reset_state()
+        GradientState._reset_state()
+        from accelerate.utils import DataLoaderConfiguration
+
+        acc = Accelerator(cpu=True, dataloader_config=DataLoaderConfiguration(split_batches=split, dispatch_batches=dispatch))
+        dl = torch.utils.data.DataLoader(loader_dataset(length, iterable), batch_size=bs, drop_last=drop_last)
+        dl = acc.prepare(dl)
+        rec = {"length": length, "bs": bs, "drop_last": drop_last, "split": split, "dispatch": dispatch,
+               "iterable": iterable, "batches": [], "end_flags": [], "metrics": []}
+        for batch in dl:
+            rec["batches"].append(batch.tolist())
+            rec["end_flags"].append(bool(acc.gradient_state.end_of_dataloader))
+            rec["metrics"].append(acc.gather_for_metrics(batch).tolist())
+        rec["remainder"] = int(dl.remainder)
+        try:
+            rec["len"] = len(dl)
+        except TypeError:
+            rec["len"] = None
+        loaders.append(rec)
+    with open(os.path.join(outdir, f"loaders_r{rank}.json"), "w") as f:
+        json.dump(loaders, f)
     PartialState().destroy_process_group()
 
 
@@ -169,6 +197,9 @@ def gen_distributed(world):
                     for k in z.files:
                         merged[f"r{r}/{k}"] = z[k]
             np.savez_compressed(os.path.join(HERE, f"ddp_w{world}_{tag}.npz"), **merged)
+        per_rank = [json.load(open(os.path.join(tmp, f"loaders_r{r}.json"))) for r in range(world)]
+        with open(os.path.join(HERE, f"loaders_w{world}.json"), "w") as f:
+            json.dump(per_rank, f, separators=(",", ":"))
     print("distributed fixtures for world", world)
 
 

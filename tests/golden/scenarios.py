@@ -43,3 +43,29 @@ def ops_inputs(rank: int, world: int):
         "bool": torch.rand(6, generator=g) > 0.5,
         "noncontig": torch.randn(4, 6, generator=g).t(),
     }
+
+
+# (dataset length, batch size, drop_last, split_batches, dispatch_batches, iterable dataset)
+LOADER_GRID = [
+    (length, bs, drop_last, split, dispatch, iterable)
+    for length in (22, 24)
+    for bs in (4,)
+    for drop_last in (False, True)
+    for split in (False, True)
+    for dispatch, iterable in ((False, False), (True, False), (None, True), (False, True))
+]
+
+
+class _Stream(torch.utils.data.IterableDataset):
+    def __init__(self, n):
+        self.n = n
+
+    def __iter__(self):
+        return iter(torch.arange(self.n).tolist())
+
+    def __len__(self):
+        return self.n
+
+
+def loader_dataset(length: int, iterable: bool):
+    return _Stream(length) if iterable else torch.arange(length)

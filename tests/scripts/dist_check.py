@@ -183,6 +183,35 @@ def main():
     assert acc.check_trigger() is True
     assert acc.check_trigger() is False
 
+    # ------------------------------------------------------------ prepared dataloaders vs the reference's
+    import json
+
+    from scenarios import loader_dataset
+
+    from accelerate_b200 import DataLoaderConfiguration
+
+    gold_loaders = json.load(open(os.path.join(ROOT, "tests", "golden", f"loaders_w{world}.json")))[rank]
+    assert len(gold_loaders) >= 20
+    for rec in gold_loaders:
+        AcceleratorState._reset_state()
+        GradientState._reset_state()
+        acc = Accelerator(cpu=cpu, dataloader_config=DataLoaderConfiguration(split_batches=rec["split"], dispatch_batches=rec["dispatch"]))
+        dl = torch.utils.data.DataLoader(loader_dataset(rec["length"], rec["iterable"]), batch_size=rec["bs"], drop_last=rec["drop_last"])
+        dl = acc.prepare(dl)
+        batches, flags, metrics = [], [], []
+        for batch in dl:
+            assert batch.device.type == dev.type
+            batches.append(batch.tolist())
+            flags.append(bool(acc.gradient_state.end_of_dataloader))
+            metrics.append(acc.gather_for_metrics(batch).tolist())
+        tag = {k: rec[k] for k in ("length", "bs", "drop_last", "split", "dispatch", "iterable")}
+        assert batches == rec["batches"], (tag, batches, rec["batches"])
+        assert flags == rec["end_flags"], (tag, flags)
+        assert metrics == rec["metrics"], (tag, metrics, rec["metrics"])
+        assert int(dl.remainder) == rec["remainder"], (tag, dl.remainder, rec["remainder"])
+        if rec["len"] is not None:
+            assert len(dl) == rec["len"], (tag, len(dl), rec["len"])
+
     if not cpu:
         PartialState().runtime.ctx.check_status()
         torch.cuda.synchronize()
