@@ -739,11 +739,12 @@ extern "C" int b200dp_allreduce_bucket(b200dp_ctx* c, int seg, size_t elem_off, 
   a.byte_off = byte_off;
   a.nvec = nbytes / 16;
   a.prescale = prescale;
+  a.flags = flags;
   const int want_slot = (flags & B200DP_F_STATS) ? slot : -1;
   if ((flags & B200DP_F_STATS) && slot < 0) return fail(B200DP_EINVAL, "B200DP_F_STATS needs a slot");
   if ((rc = make_sink(c, channel, want_slot, c->world, &a.sink))) return rc;
   const size_t per_rank = (a.nvec + c->world - 1) / c->world;
-  const int grid = clamp_blocks(c, per_rank, size_t(kThreads) * 2, max_blocks);
+  const int grid = clamp_blocks(c, per_rank, size_t(kThreads) * 4, max_blocks);
   cudaStream_t st = (cudaStream_t)stream;
   if (after_stream != B200DP_NO_STREAM && after_stream != stream) {
     if ((rc = b200dp_stream_wait(c, stream, after_stream))) return rc;
@@ -753,6 +754,17 @@ extern "C" int b200dp_allreduce_bucket(b200dp_ctx* c, int seg, size_t elem_off, 
     case B200DP_BF16: launch_allreduce<__nv_bfloat16>(a, c->world, nvls, grid, st); break;
     default: launch_allreduce<__half>(a, c->world, nvls, grid, st); break;
   }
+  KERNEL_OK(c);
+  return B200DP_OK;
+}
+
+extern "C" int b200dp_fence(b200dp_ctx* c, int channel, void* stream) {
+  if (!c) return fail(B200DP_EINVAL, "null ctx");
+  DeviceGuard g(c->device);
+  BarrierCtx b;
+  int rc = make_barrier(c, channel, &b);
+  if (rc) return rc;
+  fence_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(b);
   KERNEL_OK(c);
   return B200DP_OK;
 }

@@ -96,38 +96,30 @@ struct AllreduceArgs {
   size_t byte_off;   // bucket start inside the segment (16-byte aligned)
   size_t nvec;       // 16-byte vectors in the bucket
   float prescale;
+  int flags;         // B200DP_F_*
   StatsSink sink;
 };
 
+// Loads one 16-byte vector of the bucket from all W ranks (issued back to back: W requests in flight).
+template <int W>
+__device__ __forceinline__ void load_all_ranks(const AllreduceArgs& a, size_t byte, uint4* v) {
+#pragma unroll
+  for (int r = 0; r < W; ++r) v[r] = ld_stream16(reinterpret_cast<const char*>(a.bufs.p[r]) + byte);
+}
+
+// acc = fl(x_0 * s); acc = fl(acc + fl(x_r * s)), r ascending; returns the packed result, feeds the stats.
 template <typename T, int W>
-__device__ __forceinline__ uint4 reduce_vec_twoshot(const AllreduceArgs& a, size_t byte, float prescale, Stats& st,
-                                                    bool want_stats) {
+__device__ __forceinline__ uint4 reduce_loaded(const uint4* v, float prescale, Stats& st, bool want_stats) {
   constexpr int N = Vec16<T>::N;
   float acc[N], x[N];
-  if constexpr (W > 0) {
-    uint4 v[W];
+  Vec16<T>::unpack(v[0], acc);
 #pragma unroll
-    for (int r = 0; r < W; ++r) v[r] = ld_stream16(reinterpret_cast<const char*>(a.bufs.p[r]) + byte);
-    Vec16<T>::unpack(v[0], acc);
+  for (int k = 0; k < N; ++k) acc[k] = __fmul_rn(acc[k], prescale);
 #pragma unroll
-    for (int k = 0; k < N; ++k) acc[k] = __fmul_rn(acc[k], prescale);
+  for (int r = 1; r < W; ++r) {
+    Vec16<T>::unpack(v[r], x);
 #pragma unroll
-    for (int r = 1; r < W; ++r) {
-      Vec16<T>::unpack(v[r], x);
-#pragma unroll
-      for (int k = 0; k < N; ++k) acc[k] = __fadd_rn(acc[k], __fmul_rn(x[k], prescale));
-    }
-  } else {  // any world size
-    uint4 v0 = ld_stream16(reinterpret_cast<const char*>(a.bufs.p[0]) + byte);
-    Vec16<T>::unpack(v0, acc);
-#pragma unroll
-    for (int k = 0; k < N; ++k) acc[k] = __fmul_rn(acc[k], prescale);
-    for (int r = 1; r < a.bar.world; ++r) {
-      uint4 v = ld_stream16(reinterpret_cast<const char*>(a.bufs.p[r]) + byte);
-      Vec16<T>::unpack(v, x);
-#pragma unroll
-      for (int k = 0; k < N; ++k) acc[k] = __fadd_rn(acc[k], __fmul_rn(x[k], prescale));
-    }
+    for (int k = 0; k < N; ++k) acc[k] = __fadd_rn(acc[k], __fmul_rn(x[k], prescale));
   }
   uint4 out = Vec16<T>::pack(acc);
   if (want_stats) {
@@ -137,6 +129,37 @@ __device__ __forceinline__ uint4 reduce_vec_twoshot(const AllreduceArgs& a, size
   }
   return out;
 }
+
+// any world size: one rank at a time (less memory-level parallelism, but no W-sized register array)
+template <typename T>
+__device__ __forceinline__ uint4 reduce_vec_generic(const AllreduceArgs& a, size_t byte, float prescale, Stats& st,
+                                                    bool want_stats) {
+  constexpr int N = Vec16<T>::N;
+  float acc[N], x[N];
+  uint4 v0 = ld_stream16(reinterpret_cast<const char*>(a.bufs.p[0]) + byte);
+  Vec16<T>::unpack(v0, acc);
+#pragma unroll
+  for (int k = 0; k < N; ++k) acc[k] = __fmul_rn(acc[k], prescale);
+  for (int r = 1; r < a.bar.world; ++r) {
+    uint4 v = ld_stream16(reinterpret_cast<const char*>(a.bufs.p[r]) + byte);
+    Vec16<T>::unpack(v, x);
+#pragma unroll
+    for (int k = 0; k < N; ++k) acc[k] = __fadd_rn(acc[k], __fmul_rn(x[k], prescale));
+  }
+  uint4 out = Vec16<T>::pack(acc);
+  if (want_stats) {
+    Vec16<T>::unpack(out, x);
+#pragma unroll
+    for (int k = 0; k < N; ++k) st.add(x[k]);
+  }
+  return out;
+}
+
+// vectors a thread keeps in flight per loop trip: W x kUnroll 16-byte loads (two-shot), kUnroll (NVLS)
+template <int W>
+struct UnrollFor {
+  static constexpr int value = W >= 8 ? 2 : 4;
+};
 
 template <typename T, int W, bool NVLS>
 __global__ void __launch_bounds__(kThreads, 1) allreduce_inplace_kernel(const AllreduceArgs a) {
@@ -152,68 +175,84 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_inplace_kernel(const Al
   const size_t lo = size_t(b.rank) * per_rank;
   const size_t hi = (lo + per_rank < a.nvec) ? lo + per_rank : a.nvec;
   const size_t stride = size_t(gridDim.x) * blockDim.x;
+  const size_t first = lo + size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   Stats st;
   constexpr int N = Vec16<T>::N;
 
   if constexpr (NVLS) {
+    constexpr int U = 4;
     char* mcb = a.mc + a.byte_off;
-    for (size_t i = lo + size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < hi; i += 2 * stride) {
-      const size_t i1 = i + stride;
-      const bool two = i1 < hi;
-      uint4 s0 = MultimemOps<T>::ld_reduce(mcb + i * 16);
-      uint4 s1 = two ? MultimemOps<T>::ld_reduce(mcb + i1 * 16) : make_uint4(0, 0, 0, 0);
-      float f[N];
-      Vec16<T>::unpack(s0, f);
+    for (size_t i = first; i < hi; i += U * stride) {
+      uint4 s[U];
+      bool ok[U];
 #pragma unroll
-      for (int k = 0; k < N; ++k) f[k] = __fmul_rn(f[k], a.prescale);
-      uint4 o0 = Vec16<T>::pack(f);
-      if (want_stats) {
-        Vec16<T>::unpack(o0, f);
-#pragma unroll
-        for (int k = 0; k < N; ++k) st.add(f[k]);
+      for (int u = 0; u < U; ++u) {  // all switch-side reductions of this trip are in flight together
+        const size_t idx = i + u * stride;
+        ok[u] = idx < hi;
+        if (ok[u]) s[u] = MultimemOps<T>::ld_reduce(mcb + idx * 16);
       }
-      multimem_st16(mcb + i * 16, o0);
-      if (two) {
-        Vec16<T>::unpack(s1, f);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (!ok[u]) continue;
+        float f[N];
+        Vec16<T>::unpack(s[u], f);
 #pragma unroll
         for (int k = 0; k < N; ++k) f[k] = __fmul_rn(f[k], a.prescale);
-        uint4 o1 = Vec16<T>::pack(f);
+        const uint4 o = Vec16<T>::pack(f);
         if (want_stats) {
-          Vec16<T>::unpack(o1, f);
+          Vec16<T>::unpack(o, f);
 #pragma unroll
           for (int k = 0; k < N; ++k) st.add(f[k]);
         }
-        multimem_st16(mcb + i1 * 16, o1);
+        multimem_st16(mcb + (i + u * stride) * 16, o);
+      }
+    }
+  } else if constexpr (W > 0) {
+    constexpr int U = UnrollFor<W>::value;
+    for (size_t i = first; i < hi; i += U * stride) {
+      uint4 v[U][W];
+      bool ok[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const size_t idx = i + u * stride;
+        ok[u] = idx < hi;
+        if (ok[u]) load_all_ranks<W>(a, a.byte_off + idx * 16, v[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (!ok[u]) continue;
+        const uint4 o = reduce_loaded<T, W>(v[u], a.prescale, st, want_stats);
+        const size_t byte = a.byte_off + (i + u * stride) * 16;
+#pragma unroll
+        for (int r = 0; r < W; ++r) st_stream16(reinterpret_cast<char*>(a.bufs.p[r]) + byte, o);
       }
     }
   } else {
-    for (size_t i = lo + size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < hi; i += 2 * stride) {
-      const size_t i1 = i + stride;
-      const bool two = i1 < hi;
-      const size_t byte0 = a.byte_off + i * 16, byte1 = a.byte_off + i1 * 16;
-      uint4 o0 = reduce_vec_twoshot<T, W>(a, byte0, a.prescale, st, want_stats);
-      uint4 o1 = make_uint4(0, 0, 0, 0);
-      if (two) o1 = reduce_vec_twoshot<T, W>(a, byte1, a.prescale, st, want_stats);
-      if constexpr (W > 0) {
-#pragma unroll
-        for (int r = 0; r < W; ++r) {
-          st_stream16(reinterpret_cast<char*>(a.bufs.p[r]) + byte0, o0);
-          if (two) st_stream16(reinterpret_cast<char*>(a.bufs.p[r]) + byte1, o1);
-        }
-      } else {
-        for (int r = 0; r < world; ++r) {
-          st_stream16(reinterpret_cast<char*>(a.bufs.p[r]) + byte0, o0);
-          if (two) st_stream16(reinterpret_cast<char*>(a.bufs.p[r]) + byte1, o1);
-        }
-      }
+    for (size_t i = first; i < hi; i += stride) {
+      const size_t byte = a.byte_off + i * 16;
+      const uint4 o = reduce_vec_generic<T>(a, byte, a.prescale, st, want_stats);
+      for (int r = 0; r < world; ++r) st_stream16(reinterpret_cast<char*>(a.bufs.p[r]) + byte, o);
     }
   }
 
   if (want_stats) publish_stats(a.sink, st);
 
+  if (a.flags & B200DP_F_NO_END_BARRIER) {
+    // a later kernel on this channel (or b200dp_fence) provides the "everything has landed" guarantee
+    __syncthreads();
+    barrier_seq_end(b, base, 1);
+    return;
+  }
   // all reduced slices (and stats records) have landed everywhere before anyone's kernel retires
   cross_rank_barrier(b, base + 2);
   barrier_seq_end(b, base, 2);
+}
+
+// barrier-only kernel (one CTA): closes a sequence of NO_END_BARRIER launches
+__global__ void __launch_bounds__(32) fence_kernel(const BarrierCtx b) {
+  const uint32_t base = barrier_seq_begin(b);
+  cross_rank_barrier(b, base + 1);
+  barrier_seq_end(b, base, 1);
 }
 
 // ------------------------------------------------------------------------------------------------

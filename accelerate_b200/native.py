@@ -32,6 +32,7 @@ HANDLE_CUDAIPC, HANDLE_POSIXFD = 0, 1
 CH_GRAD, CH_USER, CH_SMALL = 0, 1, 2
 ALGO_AUTO, ALGO_TWOSHOT, ALGO_NVLS, ALGO_ONESHOT = 0, 1, 2, 3
 F_STATS = 1
+F_NO_END_BARRIER = 2
 Q_LAUNCHES, Q_MULTICAST_OK, Q_VMM_OK, Q_STATUS, Q_SM_COUNT, Q_COMM_STREAM = range(6)
 ETIMEOUT = -4
 NO_STREAM = ctypes.c_void_p(-1).value  # B200DP_NO_STREAM: stream 0 is a real stream, so NULL cannot mean 'none'
@@ -42,7 +43,7 @@ EXPORTS = [
     "b200dp_seg_import", "b200dp_seg_peer_ptr", "b200dp_seg_destroy", "b200dp_mc_create",
     "b200dp_mc_attach", "b200dp_mc_bind", "b200dp_seg_mc_ptr", "b200dp_control_bytes",
     "b200dp_set_control", "b200dp_fdx_open", "b200dp_fdx_send", "b200dp_fdx_recv", "b200dp_fdx_close",
-    "b200dp_stream_wait", "b200dp_allreduce_bucket", "b200dp_allreduce_oneshot", "b200dp_finalize_norm",
+    "b200dp_stream_wait", "b200dp_fence", "b200dp_allreduce_bucket", "b200dp_allreduce_oneshot", "b200dp_finalize_norm",
     "b200dp_scale_flat", "b200dp_clamp_flat", "b200dp_multi_stats", "b200dp_multi_scale", "b200dp_pack",
     "b200dp_pull", "b200dp_exchange_small", "b200dp_pad_copy",
 ]  # fmt: skip
@@ -142,6 +143,7 @@ def load():
             "b200dp_fdx_recv": [vp, POINTER(i), POINTER(i), i],
             "b200dp_fdx_close": [vp],
             "b200dp_stream_wait": [vp, vp, vp],
+            "b200dp_fence": [vp, i, vp],
             "b200dp_allreduce_bucket": [vp, i, sz, sz, i, c_float, i, i, i, i, i, vp, vp],
             "b200dp_allreduce_oneshot": [vp, i, sz, sz, i, c_double, vp, i, i, vp],
             "b200dp_finalize_norm": [vp, i, i, i, c_double, c_float, vp, vp, vp],
@@ -279,6 +281,9 @@ class Context:
     # -- data path --
     def stream_wait(self, waiter: int, signaller: int):
         _check(self.lib, self.lib.b200dp_stream_wait(self.h, waiter, signaller), "b200dp_stream_wait")
+
+    def fence(self, channel: int, stream: int):
+        _check(self.lib, self.lib.b200dp_fence(self.h, channel, stream), "b200dp_fence")
 
     def allreduce_bucket(self, seg, elem_off, count, dtype, prescale, slot, flags, algo, channel, max_blocks,
                          after_stream, stream):  # fmt: skip

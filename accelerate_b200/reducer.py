@@ -53,6 +53,7 @@ _LIVE = weakref.WeakSet()
 _DEBUG = os.environ.get("B200DP_DEBUG", "0") == "1"
 _KEEP_STAGED = os.environ.get("B200DP_KEEP_STAGED", "0") == "1"
 _SAME_STREAM = os.environ.get("B200DP_SAME_STREAM", "0") == "1"
+_NVLS_MIN_WORLD = int(os.environ.get("B200DP_NVLS_MIN_WORLD", "4"))
 
 
 def live_reducers():
@@ -146,6 +147,7 @@ class GradReducer:
         self.num_reductions = 0  # sync-backwards completed (tests / bench introspection)
         self.compute_stream = 0
         self._graveyard = []
+        self._comm_dirty = False
         self.rt = None
         if self.is_cuda:
             from .runtime import SymmRuntime, native_dtype
@@ -269,10 +271,14 @@ class GradReducer:
             seg = b.group.segment
             algo = self.algo
             if algo == native.ALGO_AUTO:
-                algo = native.ALGO_NVLS if (seg.multicast and self.world > 1) else native.ALGO_TWOSHOT
+                # measured on B200 (profiles/): with 2 ranks the switch has nothing to save and plain peer
+                # loads/stores stream faster; from 4 ranks on NVLS moves ~S instead of 2(N-1)/N*S per GPU
+                algo = native.ALGO_NVLS if (seg.multicast and self.world >= _NVLS_MIN_WORLD) else native.ALGO_TWOSHOT
             comm = cs if _SAME_STREAM else self.comm_stream
             ctx.allreduce_bucket(seg.seg, b.elem_off, b.count, b.group.native_dtype, 1.0 / self.world, b.slot,
-                                 native.F_STATS, algo, native.CH_GRAD, self.max_blocks, cs, comm)  # fmt: skip
+                                 native.F_STATS | native.F_NO_END_BARRIER, algo, native.CH_GRAD, self.max_blocks, cs,
+                                 comm)  # fmt: skip
+            self._comm_dirty = True
         else:
             for i, g in b.staged:
                 b.views[i].copy_(g)
@@ -288,6 +294,11 @@ class GradReducer:
             if self._next < len(self.buckets):
                 self._handle_unready()
             if self.is_cuda:
+                if self._comm_dirty:
+                    # bucket kernels skip their closing barrier; ONE fence per backward proves that every
+                    # peer's stores into this rank's fusion buffer (and statistics records) have landed
+                    self.rt.ctx.fence(native.CH_GRAD, self.compute_stream if _SAME_STREAM else self.comm_stream)
+                    self._comm_dirty = False
                 # the optimizer (compute stream) must see the reduced gradients
                 if not _SAME_STREAM:
                     self.rt.ctx.stream_wait(self.compute_stream, self.comm_stream)

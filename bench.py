@@ -182,14 +182,34 @@ def run_reference_arm(args):
         "e2e": {"value": leg["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }  # fmt: skip
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Libraries (NCCL's version banner, transformers notices) write to fd 1; the contract is ONE JSON line
+    on stdout, so everything else is routed to stderr and the JSON goes to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
     args = parse()
+    quiet_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
         return
@@ -308,7 +328,7 @@ def main():
             line["torch_ddp_nccl"] = ddp_leg
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        emit(line)
     acc.wait_for_everyone()
     PartialState().destroy_process_group()
 
@@ -365,7 +385,11 @@ def kernel_roofline(acc, model, rt, world, peaks, peak_src):
     red = model.reducer
     group = next(iter(red.groups.values()))
     count = min(25 * 1024 * 1024 // 4, group.total_elems // 4 * 4)
-    algo = native.ALGO_NVLS if group.segment.multicast else native.ALGO_TWOSHOT
+    from accelerate_b200 import reducer as _red
+
+    algo = red.algo
+    if algo == native.ALGO_AUTO:
+        algo = native.ALGO_NVLS if (group.segment.multicast and world >= _red._NVLS_MIN_WORLD) else native.ALGO_TWOSHOT
     sizes = {}
     for label, cnt in (("bucket_25MiB", count), ("all_grads", group.total_elems // 4 * 4)):
         acc.wait_for_everyone()

@@ -74,6 +74,9 @@ extern "C" {
 
 /* flags for b200dp_allreduce_bucket */
 #define B200DP_F_STATS 1 /* accumulate sum-of-squares / max-abs / non-finite into the slot record */
+#define B200DP_F_NO_END_BARRIER 2 /* skip the closing cross-rank barrier: legal when another kernel of the
+                                   * same channel/stream follows (its opening barrier proves the peers finished
+                                   * this one); the LAST kernel of a sequence must be followed by b200dp_fence */
 
 /* b200dp_query keys */
 #define B200DP_Q_LAUNCHES 0      /* kernels launched by this context so far */
@@ -146,6 +149,11 @@ int b200dp_stream_wait(b200dp_ctx* ctx, void* waiter, void* signaller);
 int b200dp_allreduce_bucket(b200dp_ctx* ctx, int seg, size_t elem_off, size_t count, int dtype,
                             float prescale, int slot, int flags, int algo, int channel,
                             int max_blocks, void* after_stream, void* stream);
+
+/* one-CTA cross-rank barrier on `channel`: when it retires on this rank, every peer has finished every
+ * earlier kernel of that channel (so all their stores into this rank's memory have landed).  Closes a
+ * sequence of B200DP_F_NO_END_BARRIER launches (the reducer issues it once per backward). */
+int b200dp_fence(b200dp_ctx* ctx, int channel, void* stream);
 
 /* out-of-place one-shot: dst_i = sum_r staging_r[i] (rank order) then / divisor (true division
  * for floating types; divisor 1 = plain sum).  Replaces operations.reduce's
