@@ -23,6 +23,11 @@ from .runtime import SymmRuntime, native_dtype
 ONESHOT_MAX_BYTES = 512 * 1024
 
 
+def _bulk_capacity(rt, staging) -> int:
+    """Bytes of the staging segment usable by the stage-then-pull/reduce path (the tail belongs to b200dp_push)."""
+    return (staging.nbytes - rt.ctx.push_area_bytes()) // 16 * 16
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -50,7 +55,10 @@ def all_gather(t: torch.Tensor) -> torch.Tensor:
         return out
     staging = rt.ensure_staging()
     st = _stream()
-    cap = staging.nbytes // 16 * 16
+    if nbytes <= rt.push_max:  # latency path: one launch, one cross-GPU barrier
+        rt.ctx.push(staging.seg, 0, t.data_ptr(), nbytes, native.U8, 1.0, out.data_ptr(), native.CH_PUSH, st)
+        return out
+    cap = _bulk_capacity(rt, staging)
     src, dst = t.data_ptr(), out.data_ptr()
     done = 0
     while done < nbytes:
@@ -84,7 +92,10 @@ def all_reduce(t: torch.Tensor, mean: bool = False) -> torch.Tensor:
     nbytes = numel * es
     divisor = float(world) if mean else 1.0
     fused_types = (torch.float32, torch.bfloat16, torch.float16)
-    cap_elems = (staging.nbytes // 16 * 16) // es
+    if nbytes <= rt.push_max:  # latency path: one launch, one cross-GPU barrier
+        rt.ctx.push(staging.seg, 1, src.data_ptr(), nbytes, dt, divisor, out.data_ptr(), native.CH_PUSH, st)
+        return out.view(t.shape)
+    cap_elems = _bulk_capacity(rt, staging) // es
     large = nbytes > ONESHOT_MAX_BYTES and src.dtype in fused_types
     done = 0
     while done < numel:
@@ -114,7 +125,7 @@ def broadcast_(t: torch.Tensor, src: int = 0) -> torch.Tensor:
     if nbytes:
         staging = rt.ensure_staging()
         st = _stream()
-        cap = staging.nbytes // 16 * 16
+        cap = _bulk_capacity(rt, staging)
         done = 0
         while done < nbytes:
             n = min(cap, nbytes - done)

@@ -1030,6 +1030,54 @@ extern "C" int b200dp_pull(b200dp_ctx* c, int seg, size_t byte_off, size_t nbyte
 }
 
 // ------------------------------------------------------------------------------------------------
+// K2b
+// ------------------------------------------------------------------------------------------------
+extern "C" size_t b200dp_push_max_bytes(void) { return size_t(kPushCtas) * kPushWindow; }
+extern "C" size_t b200dp_push_area_bytes(void) { return kPushAreaBytes; }
+
+extern "C" int b200dp_push(b200dp_ctx* c, int seg, int mode, const void* src, size_t nbytes, int dtype, double divisor,
+                           void* dst, int channel, void* stream) {
+  Segment* s;
+  int rc = get_seg(c, seg, &s);
+  if (rc) return rc;
+  if ((rc = all_mapped(c, *s))) return rc;
+  if (s->bytes < kPushAreaBytes) return fail(B200DP_EINVAL, "segment too small for the push area (%zu < %zu)", s->bytes, kPushAreaBytes);
+  if (nbytes == 0) return B200DP_OK;
+  if (nbytes > size_t(kPushCtas) * kPushWindow) return fail(B200DP_EINVAL, "push: %zu bytes exceed the %zu-byte limit", nbytes, size_t(kPushCtas) * kPushWindow);
+  if (!src || !dst) return fail(B200DP_EINVAL, "null src/dst");
+  const size_t es = mode == 1 ? dtype_size(dtype) : 1;
+  if (mode == 1 && (!es || nbytes % es)) return fail(B200DP_EINVAL, "push reduce: bad dtype/size");
+  if (mode == 1 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) % es))
+    return fail(B200DP_EINVAL, "push reduce: src/dst not aligned to the element size");
+  DeviceGuard g(c->device);
+  PushArgs a;
+  if ((rc = make_barrier(c, channel, &a.bar))) return rc;
+  fill_peers(c, *s, &a.bufs);
+  a.area_off = s->bytes - kPushAreaBytes;
+  a.src = reinterpret_cast<const char*>(src);
+  a.dst = reinterpret_cast<char*>(dst);
+  a.nbytes = nbytes;
+  a.divisor = divisor;
+  const int grid = int((nbytes + kPushWindow - 1) / kPushWindow);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mode == 0) {
+    push_kernel<0, unsigned char><<<grid, kThreads, 0, st>>>(a);
+  } else {
+    switch (dtype) {
+      case B200DP_F32: push_kernel<1, float><<<grid, kThreads, 0, st>>>(a); break;
+      case B200DP_BF16: push_kernel<1, __nv_bfloat16><<<grid, kThreads, 0, st>>>(a); break;
+      case B200DP_F16: push_kernel<1, __half><<<grid, kThreads, 0, st>>>(a); break;
+      case B200DP_F64: push_kernel<1, double><<<grid, kThreads, 0, st>>>(a); break;
+      case B200DP_I32: push_kernel<1, int><<<grid, kThreads, 0, st>>>(a); break;
+      case B200DP_I64: push_kernel<1, long long><<<grid, kThreads, 0, st>>>(a); break;
+      default: push_kernel<1, unsigned char><<<grid, kThreads, 0, st>>>(a); break;
+    }
+  }
+  KERNEL_OK(c);
+  return B200DP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // K8
 // ------------------------------------------------------------------------------------------------
 extern "C" int b200dp_exchange_small(b200dp_ctx* c, const void* host_src, int nbytes, void* host_out, void* stream) {

@@ -407,6 +407,84 @@ __global__ void __launch_bounds__(kThreads, 1) pull_kernel(const PullArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// K2b: latency path for small messages: ONE launch, ONE barrier.  Every rank pushes its data into a
+// fixed window of every peer's staging segment (posted NVLink stores), then reads all N windows
+// locally and either concatenates (gather) or sums in rank order (reduce).  Windows are private to a
+// CTA index and double-buffered by the parity of that CTA's barrier counter, so no closing barrier is
+// needed: a window is rewritten two calls later, after every peer passed the next call's barrier.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPushCtas = 32;             // CTAs (= windows) per call
+constexpr size_t kPushWindow = 16384;     // bytes per (CTA, parity, source rank)
+constexpr size_t kPushAreaBytes = size_t(kPushCtas) * 2 * B200DP_MAX_WORLD * kPushWindow;  // 16 MiB
+
+struct PushArgs {
+  BarrierCtx bar;
+  Peers bufs;        // staging segment bases
+  size_t area_off;   // start of the push area inside the staging segment
+  const char* src;   // local input, nbytes
+  char* dst;         // local output: gather: world*nbytes, reduce: nbytes
+  size_t nbytes;     // per rank
+  double divisor;    // reduce: 1 = plain sum
+};
+
+__device__ __forceinline__ char* push_window(void* base, size_t area_off, int cta, uint32_t parity, int rank) {
+  return reinterpret_cast<char*>(base) + area_off +
+         ((size_t(cta) * 2 + parity) * B200DP_MAX_WORLD + rank) * kPushWindow;
+}
+
+// MODE 0: gather (bytes).  MODE 1: reduce over elements of type T.
+template <int MODE, typename T>
+__global__ void __launch_bounds__(kThreads, 1) push_kernel(const PushArgs a) {
+  const BarrierCtx& b = a.bar;
+  const uint32_t base = barrier_seq_begin(b);
+  const uint32_t parity = base & 1u;  // this kernel is the only one that advances the counter by an odd amount
+  const size_t lo = size_t(blockIdx.x) * kPushWindow;
+  const size_t n = a.nbytes > lo ? (a.nbytes - lo < kPushWindow ? a.nbytes - lo : kPushWindow) : 0;
+  const char* src = a.src + lo;
+  const bool vec = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(a.dst) | a.nbytes) & 15) == 0;
+
+  // phase 1: my bytes -> window [cta][parity][my rank] of every rank (including mine)
+  if (vec) {
+    for (size_t i = threadIdx.x; i < (n >> 4); i += blockDim.x) {
+      const uint4 v = ld_stream16(src + i * 16);
+      for (int r = 0; r < b.world; ++r) st_stream16(push_window(a.bufs.p[r], a.area_off, blockIdx.x, parity, b.rank) + i * 16, v);
+    }
+  } else {
+    for (size_t i = threadIdx.x; i < n; i += blockDim.x) {
+      const char v = src[i];
+      for (int r = 0; r < b.world; ++r) push_window(a.bufs.p[r], a.area_off, blockIdx.x, parity, b.rank)[i] = v;
+    }
+  }
+  cross_rank_barrier(b, base + 1);
+
+  // phase 2: everything is local now
+  char* mine = reinterpret_cast<char*>(a.bufs.p[b.rank]);
+  if constexpr (MODE == 0) {
+    for (int r = 0; r < b.world; ++r) {
+      const char* w = push_window(mine, a.area_off, blockIdx.x, parity, r);
+      char* d = a.dst + size_t(r) * a.nbytes + lo;
+      if (vec) {
+        for (size_t i = threadIdx.x; i < (n >> 4); i += blockDim.x) reinterpret_cast<uint4*>(d)[i] = *reinterpret_cast<const uint4*>(w + i * 16);
+      } else {
+        for (size_t i = threadIdx.x; i < n; i += blockDim.x) d[i] = w[i];
+      }
+    }
+  } else {
+    using Tr = ElemTraits<T>;
+    using Acc = typename Tr::Acc;
+    const size_t ne = n / sizeof(T);
+    T* d = reinterpret_cast<T*>(a.dst + lo);
+    for (size_t i = threadIdx.x; i < ne; i += blockDim.x) {
+      Acc acc = Tr::up(reinterpret_cast<const T*>(push_window(mine, a.area_off, blockIdx.x, parity, 0))[i]);
+      for (int r = 1; r < b.world; ++r)
+        acc = acc + Tr::up(reinterpret_cast<const T*>(push_window(mine, a.area_off, blockIdx.x, parity, r))[i]);
+      d[i] = oneshot_finish<T>(acc, a.divisor);
+    }
+  }
+  barrier_seq_end(b, base, 1);
+}
+
+// ------------------------------------------------------------------------------------------------
 // K4: multi-tensor copy (bucket pack / unpack / staging).  One launch for a whole bucket.
 // ------------------------------------------------------------------------------------------------
 struct PackTable {

@@ -29,7 +29,7 @@ SMALL_MAX = 128
 MT_MAX = 640
 F32, BF16, F16, F64, I32, I64, U8 = range(7)
 HANDLE_CUDAIPC, HANDLE_POSIXFD = 0, 1
-CH_GRAD, CH_USER, CH_SMALL = 0, 1, 2
+CH_GRAD, CH_USER, CH_SMALL, CH_PUSH = 0, 1, 2, 3
 ALGO_AUTO, ALGO_TWOSHOT, ALGO_NVLS, ALGO_ONESHOT = 0, 1, 2, 3
 F_STATS = 1
 F_NO_END_BARRIER = 2
@@ -45,7 +45,8 @@ EXPORTS = [
     "b200dp_set_control", "b200dp_fdx_open", "b200dp_fdx_send", "b200dp_fdx_recv", "b200dp_fdx_close",
     "b200dp_stream_wait", "b200dp_fence", "b200dp_allreduce_bucket", "b200dp_allreduce_oneshot", "b200dp_finalize_norm",
     "b200dp_scale_flat", "b200dp_clamp_flat", "b200dp_multi_stats", "b200dp_multi_scale", "b200dp_pack",
-    "b200dp_pull", "b200dp_exchange_small", "b200dp_pad_copy",
+    "b200dp_pull", "b200dp_push_max_bytes", "b200dp_push_area_bytes", "b200dp_push", "b200dp_exchange_small",
+    "b200dp_pad_copy",
 ]  # fmt: skip
 
 
@@ -122,6 +123,8 @@ def load():
         lib.b200dp_version.restype = i
         lib.b200dp_last_error.restype = c_char_p
         lib.b200dp_control_bytes.restype = sz
+        lib.b200dp_push_max_bytes.restype = sz
+        lib.b200dp_push_area_bytes.restype = sz
         sig = {
             "b200dp_init": [i, i, i, POINTER(vp)],
             "b200dp_finalize": [vp],
@@ -153,6 +156,7 @@ def load():
             "b200dp_multi_scale": [vp, POINTER(vp), POINTER(sz), i, i, vp, vp],
             "b200dp_pack": [vp, POINTER(vp), POINTER(vp), POINTER(sz), i, i, vp],
             "b200dp_pull": [vp, i, sz, sz, vp, sz, i, i, i, i, vp],
+            "b200dp_push": [vp, i, i, vp, sz, i, c_double, vp, i, vp],
             "b200dp_exchange_small": [vp, vp, i, vp, vp],
             "b200dp_pad_copy": [vp, vp, vp, sz, sz, sz, sz, i, c_uint64, i, vp],
         }
@@ -341,6 +345,15 @@ class Context:
             self.lib.b200dp_pull(self.h, seg, byte_off, nbytes, dst, dst_stride, first, nranks, channel, max_blocks, stream),
             "b200dp_pull",
         )
+
+    def push(self, seg, mode, src, nbytes, dtype, divisor, dst, channel, stream):
+        _check(self.lib, self.lib.b200dp_push(self.h, seg, mode, src, nbytes, dtype, float(divisor), dst, channel, stream), "b200dp_push")
+
+    def push_max_bytes(self) -> int:
+        return self.lib.b200dp_push_max_bytes()
+
+    def push_area_bytes(self) -> int:
+        return self.lib.b200dp_push_area_bytes()
 
     def exchange_small(self, payload: bytes, stream) -> list[bytes]:
         n = len(payload)

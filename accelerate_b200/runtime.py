@@ -93,7 +93,8 @@ class SymmRuntime:
         self._pending_fds: dict[tuple[int, int], int] = {}
         self._slot_next = 0
         self.staging: Segment | None = None
-        self.staging_bytes = int(os.environ.get("B200DP_STAGING_MB", "64")) << 20
+        self.staging_bytes = max(int(os.environ.get("B200DP_STAGING_MB", "64")) << 20, 2 * self.ctx.push_area_bytes())
+        self.push_max = self.ctx.push_max_bytes() if os.environ.get("B200DP_PUSH", "1") != "0" else 0
         self.use_bulk_pack = os.environ.get("B200DP_BULK_PACK", "1") != "0"
 
         # ---- collective agreement on the handle kind / multicast ----

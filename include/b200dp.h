@@ -60,6 +60,7 @@ extern "C" {
 #define B200DP_CH_GRAD 0  /* gradient buckets (reducer's side stream) */
 #define B200DP_CH_USER 1  /* gather / reduce / broadcast on the caller's stream */
 #define B200DP_CH_SMALL 2 /* b200dp_exchange_small */
+#define B200DP_CH_PUSH 3  /* b200dp_push (its window parity is derived from this channel's counters) */
 #define B200DP_NUM_CHANNELS 4
 
 /* allreduce algorithm selectors */
@@ -200,6 +201,17 @@ int b200dp_pack(b200dp_ctx* ctx, const void* const* srcs, void* const* dsts, con
  * r in [first, first+nranks).  Bit-exact. */
 int b200dp_pull(b200dp_ctx* ctx, int seg, size_t byte_off, size_t nbytes, void* dst,
                 size_t dst_stride, int first, int nranks, int channel, int max_blocks, void* stream);
+
+/* ---- K2b: latency path (one launch, one barrier) for messages up to b200dp_push_max_bytes() per rank.
+ * Replaces all_gather_into_tensor / all_reduce for small tensors (operations.py:342,871).  The last
+ * b200dp_push_area_bytes() bytes of segment `seg` are used as per-CTA, double-buffered windows, so
+ * [0, seg_bytes - b200dp_push_area_bytes()) stays free for b200dp_pull / b200dp_allreduce_*.
+ * mode 0: dst[r*nbytes : (r+1)*nbytes] = rank r's src (any dtype; dtype ignored).
+ * mode 1: dst = sum_r src_r in rank order, then / divisor (nbytes = count * sizeof(dtype)). */
+size_t b200dp_push_max_bytes(void);
+size_t b200dp_push_area_bytes(void);
+int b200dp_push(b200dp_ctx* ctx, int seg, int mode, const void* src, size_t nbytes, int dtype, double divisor,
+                void* dst, int channel, void* stream);
 
 /* ---- K8: tiny host-visible exchange ---------------------------------------------------------
  * Replaces: the shape all-gather + .cpu() sync of pad_across_processes

@@ -34,7 +34,7 @@ def test_constants_match_header():
                             ("SMALL_MAX", "SMALL_MAX"), ("MT_MAX", "MT_MAX"), ("F32", "F32"), ("BF16", "BF16"),
                             ("F16", "F16"), ("F64", "F64"), ("I32", "I32"), ("I64", "I64"), ("U8", "U8"),
                             ("HANDLE_CUDAIPC", "HANDLE_CUDAIPC"), ("HANDLE_POSIXFD", "HANDLE_POSIXFD"),
-                            ("CH_GRAD", "CH_GRAD"), ("CH_USER", "CH_USER"), ("CH_SMALL", "CH_SMALL"),
+                            ("CH_GRAD", "CH_GRAD"), ("CH_USER", "CH_USER"), ("CH_SMALL", "CH_SMALL"), ("CH_PUSH", "CH_PUSH"), ("F_NO_END_BARRIER", "F_NO_END_BARRIER"),
                             ("ALGO_AUTO", "ALGO_AUTO"), ("ALGO_TWOSHOT", "ALGO_TWOSHOT"), ("ALGO_NVLS", "ALGO_NVLS"),
                             ("ALGO_ONESHOT", "ALGO_ONESHOT"), ("F_STATS", "F_STATS"), ("Q_LAUNCHES", "Q_LAUNCHES"),
                             ("Q_STATUS", "Q_STATUS"), ("Q_COMM_STREAM", "Q_COMM_STREAM"), ("ETIMEOUT", "ETIMEOUT")]:  # fmt: skip

@@ -240,6 +240,40 @@ def test_oneshot_pull_exchange_world1(rt):
     rt.ctx.check_status()
 
 
+def test_push_latency_path_world1(rt):
+    """b200dp_push (one launch, one barrier): gather = copy, reduce = identity / divisor at world size 1;
+    ragged sizes, misaligned source, window boundaries, double-buffer parity over repeated calls."""
+    from accelerate_b200 import native
+
+    if rt.world != 1:
+        pytest.skip("single-process test")
+    st = rt.ensure_staging()
+    limit = rt.ctx.push_max_bytes()
+    assert limit == 32 * 16384 and st.nbytes >= 2 * rt.ctx.push_area_bytes()
+    g = torch.Generator().manual_seed(4)
+    for rep in range(3):
+        for nbytes in (1, 15, 16, 4096, 16384, 16385, 100_000, limit):
+            raw = torch.randint(0, 256, (nbytes + 8,), dtype=torch.uint8, generator=g).to(rt.device)
+            for off in (0, 3):
+                src = raw[off : off + nbytes]
+                out = torch.zeros(nbytes, dtype=torch.uint8, device=rt.device)
+                rt.ctx.push(st.seg, 0, src.data_ptr(), nbytes, native.U8, 1.0, out.data_ptr(), native.CH_PUSH, stream())
+                assert torch.equal(out, src), (rep, nbytes, off)
+    for dtype, dt in [(torch.float32, native.F32), (torch.float64, native.F64), (torch.int64, native.I64),
+                      (torch.bfloat16, native.BF16), (torch.float16, native.F16), (torch.int32, native.I32)]:  # fmt: skip
+        x = (torch.randn(10_001, generator=g) * 9).to(dtype).to(rt.device)
+        out = torch.empty_like(x)
+        rt.ctx.push(st.seg, 1, x.data_ptr(), x.numel() * x.element_size(), dt, 1.0, out.data_ptr(), native.CH_PUSH, stream())
+        assert torch.equal(out, x)
+        if x.is_floating_point():
+            rt.ctx.push(st.seg, 1, x.data_ptr(), x.numel() * x.element_size(), dt, 4.0, out.data_ptr(), native.CH_PUSH, stream())
+            assert torch.equal(out, x / 4)
+    with pytest.raises(native.B200dpError, match="exceed"):
+        big = torch.zeros(limit + 16, dtype=torch.uint8, device=rt.device)
+        rt.ctx.push(st.seg, 0, big.data_ptr(), limit + 16, native.U8, 1.0, big.data_ptr(), native.CH_PUSH, stream())
+    rt.ctx.check_status()
+
+
 def test_public_ops_single_process(rt):
     """DistributedType.NO semantics of the reference: gather/pad return the input, reduce clones."""
     from accelerate_b200 import Accelerator
