@@ -62,7 +62,7 @@ def main():
     assert acc.last_clip_mode == "fused"
     ref_params = [torch.nn.Parameter(torch.empty_like(g_)) for g_ in ref_grads]
     for rp, rg in zip(ref_params, ref_grads):
-        rp.grad = rg
+        rp.grad = rg.clone()  # clip_grad_norm_ works in place: keep ref_grads untouched for the DDP comparison
     ref_tn = torch.nn.utils.clip_grad_norm_(ref_params, 1.0)
     assert abs(tn.item() - ref_tn.item()) <= 1e-5 * ref_tn.item(), (tn.item(), ref_tn.item())
     for p, rp in zip(model.parameters(), ref_params):
