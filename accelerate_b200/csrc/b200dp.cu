@@ -697,7 +697,12 @@ static int clamp_blocks(b200dp_ctx* c, size_t work_items, size_t per_block, int 
 template <typename T>
 static void launch_allreduce(const AllreduceArgs& a, int world, bool nvls, int grid, cudaStream_t st) {
   if (nvls) {
-    allreduce_inplace_kernel<T, 0, true><<<grid, kThreads, 0, st>>>(a);
+    static const int unroll = [] {
+      const char* e = getenv("B200DP_NVLS_UNROLL");
+      return (e && atoi(e) == 8) ? 8 : 4;
+    }();
+    if (unroll == 8) allreduce_inplace_kernel<T, 8, true><<<grid, kThreads, 0, st>>>(a);
+    else allreduce_inplace_kernel<T, 4, true><<<grid, kThreads, 0, st>>>(a);
     return;
   }
   switch (world) {

@@ -66,8 +66,7 @@ __device__ __forceinline__ void cross_rank_barrier(const BarrierCtx& b, uint32_t
   __syncthreads();
   if (threadIdx.x < b.world) {
     uint32_t* remote = reinterpret_cast<uint32_t*>(b.pads.p[threadIdx.x]) + pad_slot(b.channel, blockIdx.x, b.rank);
-    __threadfence_system();
-    st_release_sys(remote, val);
+    st_release_sys(remote, val);  // release at system scope: cumulative over the CTA's writes ordered by the bar.sync above
     const uint32_t* mine = reinterpret_cast<const uint32_t*>(b.pads.p[b.rank]) + pad_slot(b.channel, blockIdx.x, threadIdx.x);
     unsigned long long t0 = 0;
     uint32_t spins = 0;

@@ -161,6 +161,8 @@ struct UnrollFor {
   static constexpr int value = W >= 8 ? 2 : 4;
 };
 
+// W > 0: two-shot specialised for W ranks; W == 0: two-shot, any world size; NVLS: W is the number of
+// switch-side reductions a thread keeps in flight (4 or 8).
 template <typename T, int W, bool NVLS>
 __global__ void __launch_bounds__(kThreads, 1) allreduce_inplace_kernel(const AllreduceArgs a) {
   const BarrierCtx& b = a.bar;
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(kThreads, 1) allreduce_inplace_kernel(const Al
   constexpr int N = Vec16<T>::N;
 
   if constexpr (NVLS) {
-    constexpr int U = 4;
+    constexpr int U = W;
     char* mcb = a.mc + a.byte_off;
     for (size_t i = first; i < hi; i += U * stride) {
       uint4 s[U];

@@ -155,7 +155,10 @@ class GradReducer:
             self.rt = SymmRuntime.get()  # raises if the native runtime is not up: no fallback
             self._native_dtype = native_dtype
             self.comm_stream = self.rt.ctx.comm_stream
-            self.max_blocks = int(os.environ.get("B200DP_REDUCE_BLOCKS", "0"))
+            # CTAs per bucket kernel.  Measured on 8xB200 (profiles/r01_allreduce_n8.json): 32 CTAs stream as fast
+            # as 148 (4-16 x 16-byte requests in flight per thread) with a lower fixed cost, and they leave
+            # 116 SMs to the backward kernels the reduction overlaps with.
+            self.max_blocks = int(os.environ.get("B200DP_REDUCE_BLOCKS", "32"))
             algo = os.environ.get("B200DP_ALGO", "auto").lower()
             self.algo = {"auto": native.ALGO_AUTO, "twoshot": native.ALGO_TWOSHOT, "nvls": native.ALGO_NVLS}[algo]
         for p in params:
@@ -350,6 +353,16 @@ class GradReducer:
                 if g is None or g.data_ptr() != ptr:
                     return False
         return True
+
+    def effective_algo(self) -> str:
+        """"nvls" or "twoshot": what the bucket kernels of this reducer actually run."""
+        if not self.is_cuda:
+            return "gloo"
+        algo = self.algo
+        if algo == native.ALGO_AUTO:
+            mc = all(g.segment.multicast for g in self.groups.values())
+            algo = native.ALGO_NVLS if (mc and self.world >= _NVLS_MIN_WORLD) else native.ALGO_TWOSHOT
+        return "nvls" if algo == native.ALGO_NVLS else "twoshot"
 
     def manages(self, parameters) -> bool:
         """True iff ``parameters`` (those with grads) are exactly this reducer's parameters and their

@@ -391,21 +391,43 @@ def kernel_roofline(acc, model, rt, world, peaks, peak_src):
     if algo == native.ALGO_AUTO:
         algo = native.ALGO_NVLS if (group.segment.multicast and world >= _red._NVLS_MIN_WORLD) else native.ALGO_TWOSHOT
     sizes = {}
-    for label, cnt in (("bucket_25MiB", count), ("all_grads", group.total_elems // 4 * 4)):
+    blocks = red.max_blocks
+    flags_iso = native.F_STATS
+    flags_seq = native.F_STATS | native.F_NO_END_BARRIER
+    K = 8  # buckets back to back, the way a backward pass issues them (closing barrier replaced by ONE fence)
+
+    def isolated(cnt):
+        rt.ctx.allreduce_bucket(group.segment.seg, 0, cnt, native.F32, 1.0 / world, red.slot_base, flags_iso, algo,
+                                native.CH_GRAD, blocks, native.NO_STREAM, st)  # fmt: skip
+
+    def sequence(cnt):
+        for j in range(K):
+            rt.ctx.allreduce_bucket(group.segment.seg, j * cnt, cnt, native.F32, 1.0 / world, red.slot_base + j % len(red.buckets),
+                                    flags_seq, algo, native.CH_GRAD, blocks, native.NO_STREAM, st)  # fmt: skip
+        rt.ctx.fence(native.CH_GRAD, st)
+
+    def clock(fn, arg, per=1):
         acc.wait_for_everyone()
         for _ in range(3):
-            rt.ctx.allreduce_bucket(group.segment.seg, 0, cnt, native.F32, 1.0 / world, red.slot_base, native.F_STATS,
-                                    algo, native.CH_GRAD, 0, native.NO_STREAM, st)  # fmt: skip
+            fn(arg)
         for i in range(reps):
             ev[2 * i].record()
-            rt.ctx.allreduce_bucket(group.segment.seg, 0, cnt, native.F32, 1.0 / world, red.slot_base, native.F_STATS,
-                                    algo, native.CH_GRAD, 0, native.NO_STREAM, st)  # fmt: skip
+            fn(arg)
             ev[2 * i + 1].record()
         torch.cuda.synchronize()
-        t = torch.tensor([sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(reps)) / reps], device=dev)
-        t = acc.gather(t).max().item()
-        bus = (cnt * 4) * 2 * (world - 1) / world / (t * 1e-3) / 1e9
-        sizes[label] = {"bytes": cnt * 4, "ms": t, "busbw_GBps": bus, "algbw_GBps": cnt * 4 / (t * 1e-3) / 1e9}
+        t = torch.tensor([sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(reps)) / reps / per], device=dev)
+        return acc.gather(t).max().item()
+
+    def entry(nbytes, ms):
+        return {"bytes": nbytes, "ms": ms, "busbw_GBps": nbytes * 2 * (world - 1) / world / (ms * 1e-3) / 1e9,
+                "algbw_GBps": nbytes / (ms * 1e-3) / 1e9}  # fmt: skip
+
+    assert K * count <= group.total_elems
+    sizes["bucket_25MiB_steady"] = entry(count * 4, clock(sequence, count, per=K))
+    sizes["bucket_25MiB_isolated"] = entry(count * 4, clock(isolated, count))
+    whole = group.total_elems // 4 * 4
+    sizes["all_grads"] = entry(whole * 4, clock(isolated, whole))
+    sizes["ctas"] = blocks
     # bucket pack (what replaces DDP's per-parameter copy-in): TMA bulk vs LDG/STG, on a mid-size real bucket
     mid = sorted(red.buckets, key=lambda bk: bk.count)[len(red.buckets) // 2]
     fresh = [torch.randn_like(p) for p in mid.params]
@@ -423,11 +445,14 @@ def kernel_roofline(acc, model, rt, world, peaks, peak_src):
         pack[label] = {"ms": t, "GBps": 2 * sum(mid.nbytes) / (t * 1e-3) / 1e9}
     extra["pack_kernel"] = pack
     group.flat.zero_()
-    b = sizes["bucket_25MiB"]
+    b = sizes["bucket_25MiB_steady"]
     roof = {"kernel": f"allreduce_inplace_kernel<float,{'NVLS' if algo == native.ALGO_NVLS else 'twoshot'}>", "bound": "nvlink",
             "achieved": b["busbw_GBps"], "peak": 770.0, "unit": "GB/s", "frac": b["busbw_GBps"] / 770.0,
             "peak_source": "B200_PROFILING.md measured peer copy 770 GB/s/dir (900 nominal)", "traffic": None,
-            "bytes_per_launch": b["bytes"], "ms_per_launch": b["ms"], "frac_of_900_nominal": b["busbw_GBps"] / 900.0}  # fmt: skip
+            "bytes_per_launch": b["bytes"], "ms_per_launch": b["ms"], "frac_of_900_nominal": b["busbw_GBps"] / 900.0,
+            "how": f"{K} x 25 MiB buckets back to back on one stream exactly as a backward pass issues them (statistics on, "
+                   f"closing barrier replaced by one fence), {blocks} CTAs; time per bucket, max over ranks; bus bandwidth = "
+                   "S*2(N-1)/N/t (nccl-tests convention; NVLS moves ~S per GPU so it can exceed the link rate)"}  # fmt: skip
     extra["allreduce_sizes"] = sizes
     return roof, extra
 

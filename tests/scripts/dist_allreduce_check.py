@@ -1,6 +1,6 @@
 """Any world size: the fused bucket allreduce (two-shot and NVLS) against the oracle on seeded data, through
 the C ABI, for several sizes/dtypes; results must be identical on all ranks, two-shot bit-exact vs the
-oracle's rank-order sum, NVLS within float32 rounding of it (bit-exact when N is a power of two for fp32)."""
+oracle's rank-order sum, NVLS within float32 rounding of it (the switch adds in its own fixed order; bit-exact at N=2)."""
 import os, sys
 import numpy as np
 import torch
@@ -38,7 +38,7 @@ def main():
                 got = view.float().cpu().numpy()
                 allranks = acc.gather(view.reshape(1, -1).clone()).float().cpu().numpy()
                 assert all(allranks[0].tobytes() == allranks[r].tobytes() for r in range(world)), (name, dtype, numel, "ranks differ")
-                if name == "twoshot" or (dtype == torch.float32 and world & (world - 1) == 0):
+                if name == "twoshot" or world == 2:  # NVLS adds in the switch's own (fixed, but not rank) order
                     assert got.tobytes() == want.tobytes(), (name, dtype, numel, np.abs(got - want).max())
                 else:
                     tol = 1e-6 if dtype == torch.float32 else 2e-2

@@ -123,7 +123,10 @@ def main():
             # against the oracle on THIS run's local gradients: bit-exact, any N (rank-order sum)
             locals_all = npy(acc.gather(lp.grad.reshape(1, -1)))
             want = oracle.ddp_mean_reduce([locals_all[r] for r in range(world)]).reshape(got.shape)
-            if not cpu or exact_sum:
+            switch_order = (not cpu) and model.reducer.effective_algo() == "nvls" and world > 2
+            if switch_order:  # NVLS: the NVSwitch adds the N copies in its own fixed order, not rank order
+                assert np.allclose(got, want, rtol=1e-6, atol=1e-8), f"{tag} grad {i}: NVLS result beyond fp32 rounding of the oracle"
+            elif not cpu or exact_sum:
                 assert same_bits(got, want), f"{tag} grad {i}: differs from oracle sum_r fl(g_r/N)"
             # identical on every rank
             everyone = npy(acc.gather(p.grad.reshape(1, -1)))

