@@ -870,6 +870,27 @@ extern "C" int b200dp_clamp_flat(b200dp_ctx* c, void* ptr, size_t count, int dty
   return B200DP_OK;
 }
 
+extern "C" int b200dp_cast(b200dp_ctx* c, const void* src, int src_dtype, void* dst, int dst_dtype, size_t count,
+                           float divisor, int max_blocks, void* stream) {
+  if (!c || !src || !dst) return fail(B200DP_EINVAL, "null argument");
+  if (count == 0) return B200DP_OK;
+  DeviceGuard g(c->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = stream_grid(c, count * 6, max_blocks);
+  if (src_dtype == B200DP_F32 && dst_dtype == B200DP_BF16)
+    cast_kernel<float, __nv_bfloat16><<<grid, kStreamThreads, 0, st>>>((const float*)src, (__nv_bfloat16*)dst, count, divisor);
+  else if (src_dtype == B200DP_F32 && dst_dtype == B200DP_F16)
+    cast_kernel<float, __half><<<grid, kStreamThreads, 0, st>>>((const float*)src, (__half*)dst, count, divisor);
+  else if (src_dtype == B200DP_BF16 && dst_dtype == B200DP_F32)
+    cast_kernel<__nv_bfloat16, float><<<grid, kStreamThreads, 0, st>>>((const __nv_bfloat16*)src, (float*)dst, count, divisor);
+  else if (src_dtype == B200DP_F16 && dst_dtype == B200DP_F32)
+    cast_kernel<__half, float><<<grid, kStreamThreads, 0, st>>>((const __half*)src, (float*)dst, count, divisor);
+  else
+    return fail(B200DP_EINVAL, "cast %d -> %d not supported (f32 <-> bf16/f16 only)", src_dtype, dst_dtype);
+  KERNEL_OK(c);
+  return B200DP_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // K5
 // ------------------------------------------------------------------------------------------------

@@ -800,6 +800,46 @@ __global__ void __launch_bounds__(kStreamThreads) clamp_flat_kernel(T* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
+// K6b: dtype conversion with divide, for the half-precision *wire* format (the reference's fp16/bf16
+// compress hooks: buffer.to(dtype).div_(N) before the allreduce, copy back to fp32 after;
+// src/accelerate/utils/dataclasses.py:206-216 -> torch default_hooks._compress_hook).
+// dst = Tout( float(Tout(src)) / divisor ): cast first, then divide in the narrow type, like torch.
+// ------------------------------------------------------------------------------------------------
+template <typename Tin, typename Tout>
+__global__ void __launch_bounds__(kStreamThreads) cast_kernel(const Tin* __restrict__ src, Tout* __restrict__ dst,
+                                                               size_t count, float divisor) {
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  const size_t tid = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  constexpr int G = 8;  // elements per thread-trip: 32 B of f32 <-> 16 B of bf16/f16
+  const bool aligned = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 31) == 0;
+  const size_t groups = aligned ? count / G : 0;
+  for (size_t gidx = tid; gidx < groups; gidx += stride) {
+    float f[G];
+    if constexpr (sizeof(Tin) == 4) {
+      Vec16<float>::unpack(ld_stream16(reinterpret_cast<const char*>(src) + gidx * 32), f);
+      Vec16<float>::unpack(ld_stream16(reinterpret_cast<const char*>(src) + gidx * 32 + 16), f + 4);
+    } else {
+      Vec16<Tin>::unpack(ld_stream16(reinterpret_cast<const char*>(src) + gidx * 16), f);
+    }
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+      float v = to_float<Tout>(from_float<Tout>(f[k]));
+      f[k] = divisor == 1.0f ? v : v / divisor;
+    }
+    if constexpr (sizeof(Tout) == 4) {
+      st_stream16(reinterpret_cast<char*>(dst) + gidx * 32, Vec16<float>::pack(f));
+      st_stream16(reinterpret_cast<char*>(dst) + gidx * 32 + 16, Vec16<float>::pack(f + 4));
+    } else {
+      st_stream16(reinterpret_cast<char*>(dst) + gidx * 16, Vec16<Tout>::pack(f));
+    }
+  }
+  for (size_t i = groups * G + tid; i < count; i += stride) {
+    float v = to_float<Tout>(from_float<Tout>(to_float<Tin>(src[i])));
+    dst[i] = from_float<Tout>(divisor == 1.0f ? v : v / divisor);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K7: fused pad copy.  Unit = U bytes (1,2,4,8,16); dst [outer, new_dim, inner_u], src [outer, old_dim, inner_u].
 // ------------------------------------------------------------------------------------------------
 template <typename U>

@@ -44,7 +44,7 @@ EXPORTS = [
     "b200dp_mc_attach", "b200dp_mc_bind", "b200dp_seg_mc_ptr", "b200dp_control_bytes",
     "b200dp_set_control", "b200dp_fdx_open", "b200dp_fdx_send", "b200dp_fdx_recv", "b200dp_fdx_close",
     "b200dp_stream_wait", "b200dp_fence", "b200dp_allreduce_bucket", "b200dp_allreduce_oneshot", "b200dp_finalize_norm",
-    "b200dp_scale_flat", "b200dp_clamp_flat", "b200dp_multi_stats", "b200dp_multi_scale", "b200dp_pack",
+    "b200dp_scale_flat", "b200dp_clamp_flat", "b200dp_cast", "b200dp_multi_stats", "b200dp_multi_scale", "b200dp_pack",
     "b200dp_pull", "b200dp_push_max_bytes", "b200dp_push_area_bytes", "b200dp_push", "b200dp_exchange_small",
     "b200dp_pad_copy",
 ]  # fmt: skip
@@ -152,6 +152,7 @@ def load():
             "b200dp_finalize_norm": [vp, i, i, i, c_double, c_float, vp, vp, vp],
             "b200dp_scale_flat": [vp, vp, sz, i, vp, i, vp],
             "b200dp_clamp_flat": [vp, vp, sz, i, c_float, i, vp],
+            "b200dp_cast": [vp, vp, i, vp, i, sz, c_float, i, vp],
             "b200dp_multi_stats": [vp, POINTER(vp), POINTER(sz), i, i, i, vp],
             "b200dp_multi_scale": [vp, POINTER(vp), POINTER(sz), i, i, vp, vp],
             "b200dp_pack": [vp, POINTER(vp), POINTER(vp), POINTER(sz), i, i, vp],
@@ -318,6 +319,10 @@ class Context:
 
     def clamp_flat(self, ptr, count, dtype, v, max_blocks, stream):
         _check(self.lib, self.lib.b200dp_clamp_flat(self.h, ptr, count, dtype, float(v), max_blocks, stream), "b200dp_clamp_flat")
+
+    def cast(self, src, src_dtype, dst, dst_dtype, count, divisor, max_blocks, stream):
+        _check(self.lib, self.lib.b200dp_cast(self.h, src, src_dtype, dst, dst_dtype, count, float(divisor), max_blocks, stream),
+               "b200dp_cast")  # fmt: skip
 
     def multi_stats(self, ptrs, numels, dtype, slot, stream):
         n = len(ptrs)

@@ -47,7 +47,7 @@ from . import native
 
 import weakref
 
-_ALIGN = 16  # bytes: every parameter slice and bucket starts on a 16-byte boundary
+_ALIGN = 32  # bytes: every parameter slice / bucket starts on a 32-byte boundary (16 B in the half-width wire copy)
 _LIVE = weakref.WeakSet()
 # debugging switches (diagnostics only; defaults are the product configuration)
 _DEBUG = os.environ.get("B200DP_DEBUG", "0") == "1"
@@ -122,6 +122,9 @@ class _DtypeGroup:
         self.elem_size = torch.empty((), dtype=dtype).element_size()
         self.total_elems = 0
         self.segment = None  # runtime.Segment (CUDA)
+        self.wire = None  # half-width symmetric copy used when a compress hook is registered
+        self.wire_flat = None
+        self.wire_native = None
         self.flat = None  # 1-D tensor over the whole buffer
         self.native_dtype = None
 
@@ -148,6 +151,7 @@ class GradReducer:
         self.compute_stream = 0
         self._graveyard = []
         self._comm_dirty = False
+        self._wire_dirty = False
         self.rt = None
         if self.is_cuda:
             from .runtime import SymmRuntime, native_dtype
@@ -271,6 +275,9 @@ class GradReducer:
                 if _KEEP_STAGED:
                     self._graveyard.extend(g for _, g in b.staged)
                 b.staged.clear()  # the pack is stream-ordered before any reuse of that memory
+            if self.wire_dtype is not None and b.group.wire is not None:
+                self._reduce_bucket_wire(b, cs)
+                return
             seg = b.group.segment
             algo = self.algo
             if algo == native.ALGO_AUTO:
@@ -286,10 +293,52 @@ class GradReducer:
             for i, g in b.staged:
                 b.views[i].copy_(g)
             b.staged.clear()
+            if self.wire_dtype is not None and b.flat.dtype == torch.float32:
+                # torch's compress hook: buffer.to(dtype).div_(N) -> allreduce -> copy back (default_hooks._compress_hook)
+                narrow = b.flat.to(self.wire_dtype).div_(self.world)
+                if self.world > 1:
+                    dist.all_reduce(narrow, op=dist.ReduceOp.SUM, group=self.process_group)
+                b.flat.copy_(narrow)
+                return
             # same arithmetic as DDP: pre-divide, then SUM (reducer.hpp:276,524)
             b.flat.mul_(1.0 / self.world)
             if self.world > 1:
                 dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.process_group)
+
+    def _pick_algo(self, seg):
+        algo = self.algo
+        if algo == native.ALGO_AUTO:
+            algo = native.ALGO_NVLS if (seg.multicast and self.world >= _NVLS_MIN_WORLD) else native.ALGO_TWOSHOT
+        return algo
+
+    def _reduce_bucket_wire(self, b: GradBucket, cs: int):
+        """Half-precision wire (the reference's fp16/bf16 compress hooks): cast+pre-divide the bucket into the
+        symmetric wire buffer, allreduce THERE (half the NVLink bytes, fp32 accumulation, one rounding), and
+        convert the whole buffer back once, after the fence, in ``_finalize_backward``."""
+        ctx, g = self.rt.ctx, b.group
+        comm = cs if _SAME_STREAM else self.comm_stream
+        ctx.stream_wait(comm, cs)
+        ctx.cast(g.flat.data_ptr() + b.elem_off * g.elem_size, g.native_dtype, g.wire_flat.data_ptr() + b.elem_off * 2,
+                 g.wire_native, b.count, float(self.world), 0, comm)  # fmt: skip
+        ctx.allreduce_bucket(g.wire.seg, b.elem_off, b.count, g.wire_native, 1.0, b.slot,
+                             native.F_STATS | native.F_NO_END_BARRIER, self._pick_algo(g.wire), native.CH_GRAD,
+                             self.max_blocks, native.NO_STREAM, comm)  # fmt: skip
+        self._comm_dirty = True
+        self._wire_dirty = True
+
+    def set_wire_dtype(self, dtype):
+        """Collective: allocate the half-width symmetric wire buffers (fp32 gradient groups only)."""
+        if dtype not in (torch.bfloat16, torch.float16):
+            raise ValueError(f"wire dtype must be torch.bfloat16 or torch.float16, got {dtype}")
+        self.wire_dtype = dtype
+        if not self.is_cuda:
+            return
+        for g in self.groups.values():
+            if g.dtype != torch.float32 or g.wire is not None:
+                continue
+            g.wire = self.rt.alloc_segment(max(g.total_elems * 2, _ALIGN), multicast=True)
+            g.wire_flat = g.wire.tensor(dtype, g.total_elems)
+            g.wire_native = self._native_dtype(dtype)
 
     def _finalize_backward(self):
         """Autograd-engine callback: runs once, after the last gradient of this backward."""
@@ -300,8 +349,15 @@ class GradReducer:
                 if self._comm_dirty:
                     # bucket kernels skip their closing barrier; ONE fence per backward proves that every
                     # peer's stores into this rank's fusion buffer (and statistics records) have landed
-                    self.rt.ctx.fence(native.CH_GRAD, self.compute_stream if _SAME_STREAM else self.comm_stream)
+                    comm = self.compute_stream if _SAME_STREAM else self.comm_stream
+                    self.rt.ctx.fence(native.CH_GRAD, comm)
                     self._comm_dirty = False
+                    if self._wire_dirty:  # every peer's reduced halves have landed: widen back to fp32, one launch
+                        for g in self.groups.values():
+                            if g.wire is not None:
+                                self.rt.ctx.cast(g.wire_flat.data_ptr(), g.wire_native, g.flat.data_ptr(), g.native_dtype,
+                                                 g.total_elems, 1.0, 0, comm)  # fmt: skip
+                        self._wire_dirty = False
                 # the optimizer (compute stream) must see the reduced gradients
                 if not _SAME_STREAM:
                     self.rt.ctx.stream_wait(self.compute_stream, self.comm_stream)
@@ -492,9 +548,13 @@ class B200DataParallel(torch.nn.Module):
         from .utils.dataclasses import DDPCommunicationHookType
 
         if isinstance(hook, DDPCommunicationHookType):
-            raise NotImplementedError(
-                f"comm hook {hook}: the half-precision wire format is not implemented yet (SURVEY.md §8f row 3)"
-            )
+            if hook == DDPCommunicationHookType.FP16:
+                self.reducer.set_wire_dtype(torch.float16)
+                return
+            if hook == DDPCommunicationHookType.BF16:
+                self.reducer.set_wire_dtype(torch.bfloat16)
+                return
+            raise NotImplementedError(f"comm hook {hook} is not implemented by the B200 reducer")
         raise NotImplementedError(
             "arbitrary Python communication hooks are not supported: the allreduce is a fused device kernel"
         )

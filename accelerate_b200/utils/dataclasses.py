@@ -100,8 +100,10 @@ class DDPCommunicationHookType(BaseEnum):
 class DistributedDataParallelKwargs(KwargsHandler):
     """Knobs of the gradient reducer; field-compatible with the reference (dataclasses.py:181-195).
 
-    ``comm_hook`` FP16/BF16 select a half-precision *wire* format inside the fused allreduce (the
-    reference's compress hooks, dataclasses.py:206-216); PowerSGD variants are not implemented.
+    ``comm_hook`` / ``comm_wrapper`` FP16/BF16 select a half-precision *wire* format for the fused
+    allreduce (the reference's compress hooks, dataclasses.py:206-216): gradients are cast and
+    pre-divided into a half-width symmetric buffer, reduced there, and widened back once per step.
+    PowerSGD variants are not implemented.
     """
 
     dim: int = 0

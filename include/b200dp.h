@@ -178,6 +178,12 @@ int b200dp_scale_flat(b200dp_ctx* ctx, void* ptr, size_t count, int dtype, const
 int b200dp_clamp_flat(b200dp_ctx* ctx, void* ptr, size_t count, int dtype, float v, int max_blocks,
                       void* stream);
 
+/* dst = (dst_dtype)src, then / divisor in dst_dtype (divisor 1 = plain cast); f32 <-> bf16/f16 only.
+ * The half-precision wire format of the gradient allreduce (DDPCommunicationHookType.FP16/BF16,
+ * src/accelerate/utils/dataclasses.py:206-216 -> torch default_hooks fp16/bf16_compress_hook). */
+int b200dp_cast(b200dp_ctx* ctx, const void* src, int src_dtype, void* dst, int dst_dtype, size_t count,
+                float divisor, int max_blocks, void* stream);
+
 /* ---- K5: multi-tensor variants for gradients that do not live in a segment (world_size 1,
  * parameter subsets).  ptrs/numels are host arrays of length n; same dtype for all.
  * multi_stats writes ceil(n / B200DP_MT_MAX) consecutive local records starting at `slot`

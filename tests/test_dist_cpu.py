@@ -11,3 +11,8 @@ from conftest import run_distributed
 def test_dist_check_cpu(world):
     out = run_distributed("dist_check.py", world, "--device", "cpu", timeout=600)
     assert out.count("DIST_CHECK_OK") == world, out[-3000:]
+
+
+def test_comm_hooks_cpu():
+    out = run_distributed("dist_comm_hook.py", 2, "--device", "cpu", timeout=600)
+    assert out.count("COMM_HOOK_OK") == 2, out[-3000:]

@@ -27,3 +27,9 @@ def test_gpt2_small_grads_two_ranks():
     """BASELINE.json config 2 shape: GPT-2-small-like block stack, fp32, 2 ranks, grads vs oracle + torch DDP semantics."""
     out = run_distributed("dist_gpt2.py", 2, env=ENV, timeout=1200)
     assert out.count("GPT2_CHECK_OK") == 2, out[-3000:]
+
+
+def test_comm_hooks_two_ranks():
+    """fp16/bf16 wire format (DDPCommunicationHookType) vs the fp32 wire, reference tolerance 1e-2."""
+    out = run_distributed("dist_comm_hook.py", 2, "--device", "cuda", env=ENV, timeout=900)
+    assert out.count("COMM_HOOK_OK") == 2, out[-3000:]

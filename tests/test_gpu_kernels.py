@@ -240,6 +240,23 @@ def test_oneshot_pull_exchange_world1(rt):
     rt.ctx.check_status()
 
 
+@pytest.mark.parametrize("narrow", [torch.bfloat16, torch.float16])
+def test_cast_kernel_matches_torch_compress_hook(rt, narrow):
+    """f32 -> narrow with divide (torch: buffer.to(dtype).div_(N)) and back; ragged and misaligned spans."""
+    g = torch.Generator().manual_seed(8)
+    for n, off in [(1, 0), (7, 0), (8, 0), (1000, 0), (1003, 1), (1 << 20, 0), ((1 << 20) + 5, 3)]:
+        base = (torch.randn(n + 8, generator=g) * 50).to(rt.device)
+        x = base[off : off + n]
+        for world in (1, 2, 3, 8):
+            out = torch.empty(n + 8, dtype=narrow, device=rt.device)[off : off + n]
+            rt.ctx.cast(x.data_ptr(), DT[torch.float32], out.data_ptr(), DT[narrow], n, float(world), 0, stream())
+            want = x.to(narrow).div_(world) if world != 1 else x.to(narrow)
+            assert torch.equal(out, want), (n, off, world)
+            back = torch.empty(n + 8, device=rt.device)[off : off + n]
+            rt.ctx.cast(out.data_ptr(), DT[narrow], back.data_ptr(), DT[torch.float32], n, 1.0, 0, stream())
+            assert torch.equal(back, want.float())
+
+
 def test_push_latency_path_world1(rt):
     """b200dp_push (one launch, one barrier): gather = copy, reduce = identity / divisor at world size 1;
     ragged sizes, misaligned source, window boundaries, double-buffer parity over repeated calls."""
