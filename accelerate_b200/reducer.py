@@ -54,6 +54,8 @@ _DEBUG = os.environ.get("B200DP_DEBUG", "0") == "1"
 _KEEP_STAGED = os.environ.get("B200DP_KEEP_STAGED", "0") == "1"
 _SAME_STREAM = os.environ.get("B200DP_SAME_STREAM", "0") == "1"
 _NVLS_MIN_WORLD = int(os.environ.get("B200DP_NVLS_MIN_WORLD", "4"))
+_NVLS_BLOCKS = int(os.environ.get("B200DP_NVLS_BLOCKS", "16"))
+_TWOSHOT_BLOCKS = int(os.environ.get("B200DP_TWOSHOT_BLOCKS", "32"))
 
 
 def live_reducers():
@@ -159,10 +161,11 @@ class GradReducer:
             self.rt = SymmRuntime.get()  # raises if the native runtime is not up: no fallback
             self._native_dtype = native_dtype
             self.comm_stream = self.rt.ctx.comm_stream
-            # CTAs per bucket kernel.  Measured on 8xB200 (profiles/r01_allreduce_n8.json): 32 CTAs stream as fast
-            # as 148 (4-16 x 16-byte requests in flight per thread) with a lower fixed cost, and they leave
-            # 116 SMs to the backward kernels the reduction overlaps with.
-            self.max_blocks = int(os.environ.get("B200DP_REDUCE_BLOCKS", "32"))
+            # CTAs per bucket kernel (0 = pick by algorithm).  Measured on 8xB200 (profiles/r01_sweep_n8_u4.json,
+            # r01_allreduce_n8.json): thanks to 4-16 x 16-byte requests in flight per thread, 16 CTAs (NVLS) /
+            # 32 CTAs (two-shot) stream as fast as 148 with a LOWER fixed cost per bucket, and they leave >= 116
+            # SMs to the backward kernels the reduction overlaps with.
+            self.max_blocks = int(os.environ.get("B200DP_REDUCE_BLOCKS", "0"))
             algo = os.environ.get("B200DP_ALGO", "auto").lower()
             self.algo = {"auto": native.ALGO_AUTO, "twoshot": native.ALGO_TWOSHOT, "nvls": native.ALGO_NVLS}[algo]
         for p in params:
@@ -279,14 +282,12 @@ class GradReducer:
                 self._reduce_bucket_wire(b, cs)
                 return
             seg = b.group.segment
-            algo = self.algo
-            if algo == native.ALGO_AUTO:
-                # measured on B200 (profiles/): with 2 ranks the switch has nothing to save and plain peer
-                # loads/stores stream faster; from 4 ranks on NVLS moves ~S instead of 2(N-1)/N*S per GPU
-                algo = native.ALGO_NVLS if (seg.multicast and self.world >= _NVLS_MIN_WORLD) else native.ALGO_TWOSHOT
+            # measured on B200 (profiles/): with 2 ranks the switch has nothing to save and plain peer
+            # loads/stores stream faster; from 4 ranks on NVLS moves ~S instead of 2(N-1)/N*S per GPU
+            algo = self._pick_algo(seg)
             comm = cs if _SAME_STREAM else self.comm_stream
             ctx.allreduce_bucket(seg.seg, b.elem_off, b.count, b.group.native_dtype, 1.0 / self.world, b.slot,
-                                 native.F_STATS | native.F_NO_END_BARRIER, algo, native.CH_GRAD, self.max_blocks, cs,
+                                 native.F_STATS | native.F_NO_END_BARRIER, algo, native.CH_GRAD, self.blocks_for(algo), cs,
                                  comm)  # fmt: skip
             self._comm_dirty = True
         else:
@@ -311,6 +312,11 @@ class GradReducer:
             algo = native.ALGO_NVLS if (seg.multicast and self.world >= _NVLS_MIN_WORLD) else native.ALGO_TWOSHOT
         return algo
 
+    def blocks_for(self, algo: int) -> int:
+        if self.max_blocks > 0:
+            return self.max_blocks
+        return _NVLS_BLOCKS if algo == native.ALGO_NVLS else _TWOSHOT_BLOCKS
+
     def _reduce_bucket_wire(self, b: GradBucket, cs: int):
         """Half-precision wire (the reference's fp16/bf16 compress hooks): cast+pre-divide the bucket into the
         symmetric wire buffer, allreduce THERE (half the NVLink bytes, fp32 accumulation, one rounding), and
@@ -320,9 +326,10 @@ class GradReducer:
         ctx.stream_wait(comm, cs)
         ctx.cast(g.flat.data_ptr() + b.elem_off * g.elem_size, g.native_dtype, g.wire_flat.data_ptr() + b.elem_off * 2,
                  g.wire_native, b.count, float(self.world), 0, comm)  # fmt: skip
+        algo = self._pick_algo(g.wire)
         ctx.allreduce_bucket(g.wire.seg, b.elem_off, b.count, g.wire_native, 1.0, b.slot,
-                             native.F_STATS | native.F_NO_END_BARRIER, self._pick_algo(g.wire), native.CH_GRAD,
-                             self.max_blocks, native.NO_STREAM, comm)  # fmt: skip
+                             native.F_STATS | native.F_NO_END_BARRIER, algo, native.CH_GRAD, self.blocks_for(algo),
+                             native.NO_STREAM, comm)  # fmt: skip
         self._comm_dirty = True
         self._wire_dirty = True
 
@@ -414,10 +421,7 @@ class GradReducer:
         """"nvls" or "twoshot": what the bucket kernels of this reducer actually run."""
         if not self.is_cuda:
             return "gloo"
-        algo = self.algo
-        if algo == native.ALGO_AUTO:
-            mc = all(g.segment.multicast for g in self.groups.values())
-            algo = native.ALGO_NVLS if (mc and self.world >= _NVLS_MIN_WORLD) else native.ALGO_TWOSHOT
+        algo = self._pick_algo(next(iter(self.groups.values())).segment)
         return "nvls" if algo == native.ALGO_NVLS else "twoshot"
 
     def manages(self, parameters) -> bool:

@@ -385,13 +385,9 @@ def kernel_roofline(acc, model, rt, world, peaks, peak_src):
     red = model.reducer
     group = next(iter(red.groups.values()))
     count = min(25 * 1024 * 1024 // 4, group.total_elems // 4 * 4)
-    from accelerate_b200 import reducer as _red
-
-    algo = red.algo
-    if algo == native.ALGO_AUTO:
-        algo = native.ALGO_NVLS if (group.segment.multicast and world >= _red._NVLS_MIN_WORLD) else native.ALGO_TWOSHOT
+    algo = red._pick_algo(group.segment)
     sizes = {}
-    blocks = red.max_blocks
+    blocks = red.blocks_for(algo)
     flags_iso = native.F_STATS
     flags_seq = native.F_STATS | native.F_NO_END_BARRIER
     K = 8  # buckets back to back, the way a backward pass issues them (closing barrier replaced by ONE fence)
