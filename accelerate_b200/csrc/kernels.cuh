@@ -378,8 +378,20 @@ __device__ __forceinline__ void copy_span(char* dst, const char* src, size_t nby
   const uintptr_t d = reinterpret_cast<uintptr_t>(dst);
   if ((d & 15) == 0) {
     const size_t nvec = nbytes >> 4;
-    for (size_t i = tid; i < nvec; i += nthreads)
-      reinterpret_cast<uint4*>(dst)[i] = ld_stream16(src + i * 16);
+    constexpr int U = 4;  // peer loads in flight per thread (NVLink latency is ~2-3 us)
+    for (size_t i = tid; i < nvec; i += U * nthreads) {
+      uint4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const size_t j = i + u * nthreads;
+        if (j < nvec) v[u] = ld_stream16(src + j * 16);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const size_t j = i + u * nthreads;
+        if (j < nvec) reinterpret_cast<uint4*>(dst)[j] = v[u];
+      }
+    }
     for (size_t i = (nvec << 4) + tid; i < nbytes; i += nthreads) dst[i] = src[i];
   } else if ((d & 3) == 0) {
     const size_t nw = nbytes >> 2;
