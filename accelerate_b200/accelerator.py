@@ -25,7 +25,7 @@ from types import MethodType
 
 import torch
 
-from .data_loader import DataLoaderDispatcher, prepare_data_loader, skip_first_batches
+from .data_loader import prepare_data_loader, skip_first_batches
 from .optimizer import AcceleratedOptimizer
 from .reducer import B200DataParallel, live_reducers
 from .scheduler import AcceleratedScheduler
@@ -41,9 +41,7 @@ from .utils.dataclasses import (
     KwargsHandler,
     PrecisionType,
     ProjectConfiguration,
-    RNGType,
 )
-from .utils.environment import parse_flag_from_env
 from .utils.operations import (
     convert_outputs_to_fp32,
     gather,
@@ -51,7 +49,6 @@ from .utils.operations import (
     pad_across_processes,
     recursively_apply,
     reduce,
-    send_to_device,
 )
 from .utils.other import extract_model_from_parallel, get_mixed_precision_context_manager
 

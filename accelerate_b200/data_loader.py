@@ -21,7 +21,6 @@ import torch
 from torch.utils.data import BatchSampler, DataLoader, IterableDataset, RandomSampler
 
 from .state import GradientState, PartialState
-from .utils.dataclasses import DistributedType, RNGType
 from .utils.operations import (
     broadcast,
     broadcast_object_list,

@@ -12,13 +12,10 @@ DeepSpeed, Megatron, TP/CP/SP, FP8 recipes) are out of scope for this build.
 from __future__ import annotations
 
 import copy
-import dataclasses
 import enum
-import os
-import warnings
 from dataclasses import dataclass, field
 from datetime import timedelta
-from typing import Any, Callable, Optional
+from typing import Any, Optional
 
 
 class KwargsHandler:
