@@ -16,3 +16,9 @@ def test_dist_check_cpu(world):
 def test_comm_hooks_cpu():
     out = run_distributed("dist_comm_hook.py", 2, "--device", "cpu", timeout=600)
     assert out.count("COMM_HOOK_OK") == 2, out[-3000:]
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_training_matches_single_process(world):
+    out = run_distributed("dist_training.py", world, "--device", "cpu", timeout=600)
+    assert out.count("TRAINING_OK") == world, out[-3000:]

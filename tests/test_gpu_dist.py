@@ -33,3 +33,9 @@ def test_comm_hooks_two_ranks():
     """fp16/bf16 wire format (DDPCommunicationHookType) vs the fp32 wire, reference tolerance 1e-2."""
     out = run_distributed("dist_comm_hook.py", 2, "--device", "cuda", env=ENV, timeout=900)
     assert out.count("COMM_HOOK_OK") == 2, out[-3000:]
+
+
+def test_training_matches_single_process_two_ranks():
+    """reference test_script.py:449-620 `training_check`: distributed SGD == single-process SGD (1e-6)."""
+    out = run_distributed("dist_training.py", 2, "--device", "cuda", env=ENV, timeout=900)
+    assert out.count("TRAINING_OK") == 2, out[-3000:]
