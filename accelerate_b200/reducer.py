@@ -53,6 +53,7 @@ _LIVE = weakref.WeakSet()
 _DEBUG = os.environ.get("B200DP_DEBUG", "0") == "1"
 _KEEP_STAGED = os.environ.get("B200DP_KEEP_STAGED", "0") == "1"
 _SAME_STREAM = os.environ.get("B200DP_SAME_STREAM", "0") == "1"
+_PACK_ON_COMM = os.environ.get("B200DP_PACK_ON_COMM", "1") == "1"
 _NVLS_MIN_WORLD = int(os.environ.get("B200DP_NVLS_MIN_WORLD", "4"))
 _NVLS_BLOCKS = int(os.environ.get("B200DP_NVLS_BLOCKS", "16"))
 _TWOSHOT_BLOCKS = int(os.environ.get("B200DP_TWOSHOT_BLOCKS", "32"))
@@ -267,17 +268,29 @@ class GradReducer:
         if self.is_cuda:
             ctx = self.rt.ctx
             cs = self.compute_stream
+            comm = cs if _SAME_STREAM else self.comm_stream
             if b.staged:
                 srcs = [g.data_ptr() for _, g in b.staged]
                 dsts = [b.ptrs[i] for i, _ in b.staged]
                 sizes = [b.nbytes[i] for i, _ in b.staged]
-                ctx.pack(srcs, dsts, sizes, self.rt.use_bulk_pack, cs)
+                if _PACK_ON_COMM and comm != cs:
+                    # adopt the gradients on the SIDE stream: the pack overlaps with the rest of backward instead
+                    # of sitting on the compute stream.  The source tensors must then outlive the pack, so they
+                    # are parked until the end-of-backward join (after which the compute stream is ordered behind
+                    # the side stream and the allocator may hand the memory out again).
+                    ctx.stream_wait(comm, cs)
+                    ctx.pack(srcs, dsts, sizes, self.rt.use_bulk_pack, comm)
+                    self._graveyard.extend(g for _, g in b.staged)
+                    pack_stream = comm
+                else:
+                    ctx.pack(srcs, dsts, sizes, self.rt.use_bulk_pack, cs)
+                    pack_stream = cs
                 if _DEBUG:
-                    print(f"[b200dp r{self.rank}] bucket {b.index}: pack {len(srcs)} spans on stream {cs:#x}: "
+                    print(f"[b200dp r{self.rank}] bucket {b.index}: pack {len(srcs)} spans on stream {pack_stream:#x}: "
                           f"{[(hex(s_), hex(d_), n_) for s_, d_, n_ in zip(srcs, dsts, sizes)]}", flush=True)
                 if _KEEP_STAGED:
                     self._graveyard.extend(g for _, g in b.staged)
-                b.staged.clear()  # the pack is stream-ordered before any reuse of that memory
+                b.staged.clear()  # same-stream pack: stream order protects the memory; side-stream pack: parked above
             if self.wire_dtype is not None and b.group.wire is not None:
                 self._reduce_bucket_wire(b, cs)
                 return
@@ -285,7 +298,6 @@ class GradReducer:
             # measured on B200 (profiles/): with 2 ranks the switch has nothing to save and plain peer
             # loads/stores stream faster; from 4 ranks on NVLS moves ~S instead of 2(N-1)/N*S per GPU
             algo = self._pick_algo(seg)
-            comm = cs if _SAME_STREAM else self.comm_stream
             ctx.allreduce_bucket(seg.seg, b.elem_off, b.count, b.group.native_dtype, 1.0 / self.world, b.slot,
                                  native.F_STATS | native.F_NO_END_BARRIER, algo, native.CH_GRAD, self.blocks_for(algo), cs,
                                  comm)  # fmt: skip
