@@ -9,6 +9,7 @@ __version__ = "0.1.0"
 
 from .accelerator import Accelerator
 from .data_loader import skip_first_batches
+from .local_sgd import LocalSGD
 from .optimizer import AcceleratedOptimizer
 from .reducer import B200DataParallel
 from .scheduler import AcceleratedScheduler

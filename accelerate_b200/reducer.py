@@ -478,6 +478,34 @@ class GradReducer:
             self.rt.ctx.clamp_flat(group.flat.data_ptr(), group.total_elems, group.native_dtype, clip_value, 0, st)
         self.stats_valid = False
 
+    def can_average_in_buffer(self) -> bool:
+        """The fusion buffer may be borrowed only while no live gradient is a view into it."""
+        if not self.is_cuda or self._armed:
+            return False
+        for b in self.buckets:
+            for p, ptr in zip(b.params, b.ptrs):
+                if p.grad is not None and p.grad.data_ptr() == ptr:
+                    return False
+        return True
+
+    def average_parameters_(self):
+        """LocalSGD: params <- mean over ranks, through the fusion buffer (pack, ONE allreduce, unpack, divide)."""
+        if self.world == 1:
+            return
+        ctx = self.rt.ctx
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.no_grad():
+            for group in self.groups.values():
+                mine = [(p, ptr, nb) for b in self.buckets if b.group is group for p, ptr, nb in zip(b.params, b.ptrs, b.nbytes)]
+                srcs, slots, sizes = [p.data_ptr() for p, _, _ in mine], [ptr for _, ptr, _ in mine], [nb for _, _, nb in mine]
+                ctx.pack(srcs, slots, sizes, self.rt.use_bulk_pack, st)
+                algo = self._pick_algo(group.segment)
+                ctx.allreduce_bucket(group.segment.seg, 0, group.total_elems, group.native_dtype, 1.0, -1, 0, algo,
+                                     native.CH_USER, self.blocks_for(algo), native.NO_STREAM, st)  # fmt: skip
+                ctx.pack(slots, srcs, sizes, self.rt.use_bulk_pack, st)
+                torch._foreach_div_([p.data for p, _, _ in mine], float(self.world))  # the reference's `/= N`
+                group.flat.zero_()
+
     def broadcast_parameters(self, module_params):
         """Make every rank's parameters equal rank 0's through the fusion buffers: pack, pull, unpack."""
         if self.world == 1:

@@ -22,3 +22,8 @@ def test_comm_hooks_cpu():
 def test_training_matches_single_process(world):
     out = run_distributed("dist_training.py", world, "--device", "cpu", timeout=600)
     assert out.count("TRAINING_OK") == world, out[-3000:]
+
+
+def test_local_sgd_cpu():
+    out = run_distributed("dist_local_sgd.py", 2, "--device", "cpu", timeout=600)
+    assert out.count("LOCAL_SGD_OK") == 2, out[-3000:]

@@ -39,3 +39,9 @@ def test_training_matches_single_process_two_ranks():
     """reference test_script.py:449-620 `training_check`: distributed SGD == single-process SGD (1e-6)."""
     out = run_distributed("dist_training.py", 2, "--device", "cuda", env=ENV, timeout=900)
     assert out.count("TRAINING_OK") == 2, out[-3000:]
+
+
+def test_local_sgd_two_ranks():
+    """LocalSGD parameter averaging through the fusion buffer (pack, one allreduce, unpack, divide)."""
+    out = run_distributed("dist_local_sgd.py", 2, "--device", "cuda", env=ENV, timeout=900)
+    assert out.count("LOCAL_SGD_OK") == 2, out[-3000:]
