@@ -630,6 +630,88 @@ class Accelerator:
         if self.is_main_process:
             torch.save(obj, f)
 
+    # ------------------------------------------------------------------ checkpoint / resume
+    def register_for_checkpointing(self, *objects):
+        """Objects with ``state_dict`` / ``load_state_dict`` that save_state/load_state should carry along."""
+        bad = [f"\t- Item at index {i}, `{type(o).__name__}`" for i, o in enumerate(objects)
+               if not (hasattr(o, "state_dict") and hasattr(o, "load_state_dict"))]  # fmt: skip
+        if bad:
+            raise ValueError("All `objects` must include a `state_dict` and `load_state_dict` function to be stored. "
+                             "The following inputs are invalid:\n" + "\n".join(bad))  # fmt: skip
+        self._custom_objects.extend(objects)
+
+    def save_state(self, output_dir: str = None, safe_serialization: bool = True, **save_model_func_kwargs):
+        """Write models, optimizers, schedulers, scaler, RNG states (every rank) and registered objects in the
+        reference's on-disk layout (accelerator.py:3579-3712)."""
+        from .checkpointing import rotate_checkpoints, save_accelerator_state, save_custom_state
+
+        cfg = self.project_configuration
+        if cfg.automatic_checkpoint_naming:
+            output_dir = os.path.join(self.project_dir, "checkpoints")
+        if output_dir is None:
+            raise ValueError("`output_dir` is required unless `automatic_checkpoint_naming` is enabled")
+        os.makedirs(output_dir, exist_ok=True)
+        if cfg.automatic_checkpoint_naming:
+            if self.is_main_process:
+                rotate_checkpoints(output_dir, cfg.total_limit)
+            output_dir = os.path.join(output_dir, f"checkpoint_{cfg.iteration}")
+            if os.path.exists(output_dir):
+                raise ValueError(f"Checkpoint directory {output_dir} ({cfg.iteration}) already exists. Please manually "
+                                 "override `self.save_iteration` with what iteration to start with.")  # fmt: skip
+            self.wait_for_everyone()
+        os.makedirs(output_dir, exist_ok=True)
+        weights = [self.get_state_dict(m, unwrap=False) for m in self._models]
+        save_accelerator_state(
+            output_dir, weights, [o for o in self._optimizers], [s for s in self._schedulers], self._dataloaders,
+            self.process_index, self.step, scaler=self.scaler, save_on_each_node=cfg.save_on_each_node,
+            safe_serialization=safe_serialization, is_main_process=self.is_main_process,
+            is_local_main_process=self.is_local_main_process,
+        )  # fmt: skip
+        writer = self.is_local_main_process if cfg.save_on_each_node else self.is_main_process
+        for i, obj in enumerate(self._custom_objects):
+            save_custom_state(obj, output_dir, i, is_writer=writer)
+        cfg.iteration += 1
+        self.wait_for_everyone()
+        return output_dir
+
+    def load_state(self, input_dir: str = None, load_kwargs: dict = None, **load_model_func_kwargs):
+        """Restore what save_state wrote (also checkpoints written by the reference; accelerator.py:3745-3895)."""
+        from .checkpointing import load_accelerator_state, load_custom_state
+
+        if input_dir is not None:
+            input_dir = os.path.expanduser(input_dir)
+            if not os.path.isdir(input_dir):
+                raise ValueError(f"Tried to find {input_dir} but folder does not exist")
+        elif self.project_configuration.automatic_checkpoint_naming:
+            folder = os.path.join(self.project_dir, "checkpoints")
+            names = sorted(os.listdir(folder), key=lambda n: int(n.rsplit("_", 1)[-1]))
+            input_dir = os.path.join(folder, names[-1])
+        else:
+            raise ValueError("No input_dir provided and automatic checkpoint naming is disabled.")
+        map_location = load_model_func_kwargs.pop("map_location", None)
+        if map_location is None:
+            map_location = "on_device" if self.num_processes > 1 and self.device.type == "cuda" else "cpu"
+        overrides = load_accelerator_state(
+            input_dir, self._models, self._optimizers, self._schedulers, self._dataloaders, self.process_index,
+            scaler=self.scaler, map_location=map_location, device=self.device, **load_model_func_kwargs,
+        )  # fmt: skip
+        if "step" in overrides:
+            self.step = overrides["step"]
+        for i, obj in enumerate(self._custom_objects):
+            load_custom_state(obj, input_dir, i)
+        self.wait_for_everyone()
+
+    def save_model(self, model, save_directory, safe_serialization: bool = True):
+        """Unwrapped weights in one file (``model.safetensors`` / ``pytorch_model.bin``), main process only."""
+        from pathlib import Path
+
+        from .checkpointing import MODEL_NAME, SAFE_MODEL_NAME, _write
+
+        os.makedirs(save_directory, exist_ok=True)
+        name = f"{SAFE_MODEL_NAME}.safetensors" if safe_serialization else f"{MODEL_NAME}.bin"
+        _write(self.get_state_dict(model), Path(save_directory) / name, self.is_main_process, safe=safe_serialization)
+        self.wait_for_everyone()
+
     def end_training(self):
         self.state.destroy_process_group()
 
