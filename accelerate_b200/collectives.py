@@ -184,3 +184,44 @@ def pad_to_max(t: torch.Tensor, dim: int, pad_index, pad_first: bool) -> torch.T
     rt.ctx.pad_copy(src.data_ptr() if src.numel() else None, out.data_ptr(), outer, src.shape[dim], max_size, inner * es,
                     es, pad_bits, pad_first, _stream())  # fmt: skip
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# object collectives: pickled bytes over the same kernels (SURVEY.md §8f row 2; reference:
+# operations.py:492-517 all_gather_object, :669-690 broadcast_object_list)
+# ---------------------------------------------------------------------------------------------
+def _exchange_lengths(n: int) -> list[int]:
+    import struct
+
+    rt = SymmRuntime.get()
+    return [struct.unpack("<q", p)[0] for p in rt.ctx.exchange_small(struct.pack("<q", n), _stream())]
+
+
+def gather_object(obj) -> list:
+    """[rank 0's obj, rank 1's obj, ...]: lengths by the 1-CTA shape exchange, payload by the allgather kernels."""
+    import pickle
+
+    rt = SymmRuntime.get()
+    payload = pickle.dumps(obj)
+    lengths = _exchange_lengths(len(payload))
+    width = (max(lengths) + 15) // 16 * 16
+    buf = torch.zeros(width, dtype=torch.uint8)
+    buf[: len(payload)] = torch.frombuffer(bytearray(payload), dtype=torch.uint8)
+    gathered = all_gather(buf.to(rt.device).reshape(1, width)).cpu()
+    return [pickle.loads(gathered[r, : lengths[r]].numpy().tobytes()) for r in range(rt.world)]
+
+
+def broadcast_object(obj, src: int = 0):
+    """Every rank returns rank ``src``'s object."""
+    import pickle
+
+    rt = SymmRuntime.get()
+    payload = pickle.dumps(obj) if rt.rank == src else b""
+    n = _exchange_lengths(len(payload))[src]
+    width = (n + 15) // 16 * 16
+    buf = torch.zeros(width, dtype=torch.uint8)
+    if rt.rank == src:
+        buf[:n] = torch.frombuffer(bytearray(payload), dtype=torch.uint8)
+    dev = buf.to(rt.device)
+    broadcast_(dev, src)
+    return obj if rt.rank == src else pickle.loads(dev.cpu()[:n].numpy().tobytes())

@@ -8,8 +8,8 @@ Dispatch is by the *process state*, never by try/except:
 * ``DistributedType.MULTI_CPU``    -> ``torch.distributed`` over gloo, exactly what the reference does
   on CPU (``operations.py:345-350``); it exists so host logic is testable without a GPU.
 
-Object collectives (``gather_object`` / ``broadcast_object_list``) stay on ``torch.distributed``
-(SURVEY.md §2c marks them "keep on torch").
+Object collectives (``gather_object`` / ``broadcast_object_list``) move pickled bytes over the same P2P
+kernels on CUDA and stay on ``torch.distributed`` for gloo.
 """
 
 from __future__ import annotations
@@ -238,11 +238,17 @@ def gather(tensor):
 
 
 def gather_object(object: Any):
+    """Gather picklable objects; like the reference, each rank passes a LIST and the lists are concatenated."""
     state = PartialState()
     if state.distributed_type == DistributedType.NO:
         return object
-    parts = [None] * state.num_processes
-    dist.all_gather_object(parts, object)
+    if state.distributed_type == DistributedType.MULTI_GPU:
+        from ..collectives import gather_object as p2p_gather_object
+
+        parts = p2p_gather_object(object)
+    else:
+        parts = [None] * state.num_processes
+        dist.all_gather_object(parts, object)
     return [item for part in parts for item in part]
 
 
@@ -265,7 +271,14 @@ def broadcast(tensor, from_process: int = 0):
 
 
 def broadcast_object_list(object_list, from_process: int = 0):
-    if PartialState().distributed_type != DistributedType.NO:
+    """In place: every rank's list becomes ``from_process``'s (operations.py:669-690)."""
+    state = PartialState()
+    if state.distributed_type == DistributedType.MULTI_GPU:
+        from ..collectives import broadcast_object
+
+        received = broadcast_object(list(object_list), src=from_process)
+        object_list[:] = received
+    elif state.distributed_type != DistributedType.NO:
         dist.broadcast_object_list(object_list, src=from_process)
     return object_list
 

@@ -87,6 +87,14 @@ def main():
     full = torch.ones(3, 2, device=dev)
     assert acc.pad_across_processes(full, dim=0) is full, "already-max tensors come back as the same object"
     assert acc.pad_across_processes(full, dim=5) is full
+    # object collectives (pickled bytes; reference tests/test_utils.py, test_script.py gather_object checks)
+    from accelerate_b200.utils import broadcast_object_list, gather_object
+
+    objs = gather_object([{"rank": rank, "payload": "x" * (10 + 300 * rank)}, rank * 1.5])
+    assert objs == [item for r in range(world) for item in ({"rank": r, "payload": "x" * (10 + 300 * r)}, r * 1.5)], objs
+    box = [("from", rank), {"k": list(range(rank + 3))}]
+    ret = broadcast_object_list(box, from_process=world - 1)
+    assert ret is box and box == [("from", world - 1), {"k": list(range(world + 2))}], box
     # oracle agrees with the reference on the same inputs (sanity of the checker itself)
     per_rank = [ops_inputs(r, world)["f32"].numpy() for r in range(world)]
     assert same_bits(oracle.gather(per_rank), gold_ops[f"r{rank}/gather/f32"])
