@@ -1,0 +1,55 @@
+#!/usr/bin/env python
+"""Single-GPU probe that launches each hot kernel a few times on realistic sizes so `ncu --set full` can capture
+it (multi-rank commands must not be wrapped in ncu).  World size 1: the allreduce kernel's NVLink side is absent,
+its HBM side (read S, write S, statistics) is what the capture shows.
+
+    ncu --set full --clock-control none --import-source on -k regex:"allreduce_inplace|pack_bulk|pack_kernel|scale_flat|push_kernel" \
+        -c 12 -o gpurun_out/prof_r01_kernels python benchmarks/kernel_probe.py
+"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    from accelerate_b200 import native
+    from accelerate_b200.state import PartialState
+
+    rt = PartialState().runtime
+    st = torch.cuda.current_stream().cuda_stream
+    n = 25 * 1024 * 1024 // 4  # one 25 MiB fp32 bucket
+    seg = rt.alloc_segment(8 * n * 4, multicast=False)
+    flat = seg.tensor(torch.float32, 8 * n)
+    flat.normal_()
+    slot = rt.reserve_slots(8)
+    out = torch.empty(3, device=rt.device)
+    grads = [torch.randn(1024, 1024, device=rt.device) for _ in range(24)] + [torch.randn(1024, device=rt.device) for _ in range(8)]
+    sizes = [g.numel() * 4 for g in grads]
+    dsts, off = [], 0
+    for s in sizes:
+        dsts.append(flat.data_ptr() + off)
+        off += (s + 31) // 32 * 32
+    small = torch.randn(4096, device=rt.device)
+    staging = rt.ensure_staging()
+    small_out = torch.empty_like(small)
+    for rep in range(3):
+        for j in range(4):  # the steady-state sequence of a backward: stats on, no closing barrier
+            rt.ctx.allreduce_bucket(seg.seg, j * n, n, native.F32, 0.125, slot + j, native.F_STATS | native.F_NO_END_BARRIER,
+                                    native.ALGO_TWOSHOT, native.CH_GRAD, 16, native.NO_STREAM, st)
+        rt.ctx.fence(native.CH_GRAD, st)
+        rt.ctx.finalize_norm(slot, 4, True, 2.0, 1.0, None, out.data_ptr(), st)
+        rt.ctx.scale_flat(flat.data_ptr(), 4 * n, native.F32, out.data_ptr() + 4, 0, st)
+        rt.ctx.pack([g.data_ptr() for g in grads], dsts, sizes, 1, st)
+        rt.ctx.pack([g.data_ptr() for g in grads], dsts, sizes, 0, st)
+        rt.ctx.push(staging.seg, 1, small.data_ptr(), small.numel() * 4, native.F32, 1.0, small_out.data_ptr(), native.CH_PUSH, st)
+    torch.cuda.synchronize()
+    rt.ctx.check_status()
+    print("probe ok")
+
+
+if __name__ == "__main__":
+    main()
