@@ -705,11 +705,16 @@ static void launch_allreduce(const AllreduceArgs& a, int world, bool nvls, int g
     else allreduce_inplace_kernel<T, 4, true><<<grid, kThreads, 0, st>>>(a);
     return;
   }
-  switch (world) {
+  switch (world) {  // W ranks known at compile time: all W loads of a vector are issued back to back
+    case 1: allreduce_inplace_kernel<T, 1, false><<<grid, kThreads, 0, st>>>(a); break;
     case 2: allreduce_inplace_kernel<T, 2, false><<<grid, kThreads, 0, st>>>(a); break;
+    case 3: allreduce_inplace_kernel<T, 3, false><<<grid, kThreads, 0, st>>>(a); break;
     case 4: allreduce_inplace_kernel<T, 4, false><<<grid, kThreads, 0, st>>>(a); break;
+    case 5: allreduce_inplace_kernel<T, 5, false><<<grid, kThreads, 0, st>>>(a); break;
+    case 6: allreduce_inplace_kernel<T, 6, false><<<grid, kThreads, 0, st>>>(a); break;
+    case 7: allreduce_inplace_kernel<T, 7, false><<<grid, kThreads, 0, st>>>(a); break;
     case 8: allreduce_inplace_kernel<T, 8, false><<<grid, kThreads, 0, st>>>(a); break;
-    default: allreduce_inplace_kernel<T, 0, false><<<grid, kThreads, 0, st>>>(a); break;
+    default: allreduce_inplace_kernel<T, 0, false><<<grid, kThreads, 0, st>>>(a); break;  // 9..16 ranks
   }
 }
 

@@ -158,7 +158,7 @@ __device__ __forceinline__ uint4 reduce_vec_generic(const AllreduceArgs& a, size
 // vectors a thread keeps in flight per loop trip: W x kUnroll 16-byte loads (two-shot), kUnroll (NVLS)
 template <int W>
 struct UnrollFor {
-  static constexpr int value = W >= 8 ? 2 : 4;
+  static constexpr int value = W >= 5 ? 2 : 4;  // keeps W x U x 4 data registers <= 64
 };
 
 // W > 0: two-shot specialised for W ranks; W == 0: two-shot, any world size; NVLS: W is the number of
