@@ -1,0 +1,111 @@
+"""Host logic of the reducer without any communication (one process, CPU transport): bucket table vs torch's own
+assignment, fusion-buffer layout, gradients-as-views life cycle, forward-time sync latch, unused parameters,
+wrapper attributes the reference's tests read (tests/test_kwargs_handlers.py:173-202)."""
+
+import pytest
+import torch
+import torch.distributed as dist
+
+from accelerate_b200.reducer import B200DataParallel, compute_bucket_assignment
+
+
+def test_bucket_assignment_matches_torch_mixed_dtypes():
+    g = torch.Generator().manual_seed(3)
+    counts = torch.randint(1, 2_000_000, (120,), generator=g).tolist()
+    dtypes = [torch.float32 if i % 5 else torch.bfloat16 for i in range(len(counts))]
+    tensors = [torch.empty(n, dtype=dt, device="meta") for n, dt in zip(counts, dtypes)]
+    sizes = [t.numel() * t.element_size() for t in tensors]
+    for first, cap in [(1 << 20, 25 << 20), (15 << 20, 15 << 20), (1 << 10, 1 << 12)]:
+        want, _ = dist._compute_bucket_assignment_by_size(tensors, [first, cap])
+        assert compute_bucket_assignment(sizes, dtypes, first, cap) == want
+
+
+def small_model():
+    torch.manual_seed(0)
+    return torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.ReLU(), torch.nn.Linear(7, 3))
+
+
+def test_wrapper_attributes_and_layout():
+    ddp = B200DataParallel(small_model(), bucket_cap_mb=15, find_unused_parameters=True, broadcast_buffers=False,
+                           gradient_as_bucket_view=True)  # fmt: skip
+    assert ddp.bucket_bytes_cap // 2**20 == 15 and ddp.find_unused_parameters and ddp.dim == 0
+    assert ddp.broadcast_buffers is False and ddp.gradient_as_bucket_view is True
+    assert ddp.require_backward_grad_sync and ddp.require_forward_param_sync
+    assert list(ddp.state_dict()) == ["module.0.weight", "module.0.bias", "module.2.weight", "module.2.bias"]
+    default = B200DataParallel(small_model())
+    assert default.bucket_bytes_cap == 25 * 2**20 and default.bucket_bytes_cap_default
+    red = default.reducer
+    assert len(red.buckets) == 1 and [p.shape for p in red.buckets[0].params] == [(3,), (3, 7), (7,), (7, 5)]
+    for b in red.buckets:  # every slice starts on a 32-byte boundary, padding is zero
+        assert all(off % 8 == 0 for off in b.offsets) and b.count % 8 == 0
+    assert float(next(iter(red.groups.values())).flat.abs().sum()) == 0.0
+    with pytest.raises(RuntimeError, match="doesn't have any parameter"):
+        B200DataParallel(torch.nn.ReLU())
+
+
+def test_views_no_sync_and_latch():
+    ddp = B200DataParallel(small_model())
+    red = ddp.reducer
+    x = torch.randn(4, 5)
+    ddp(x).sum().backward()
+    assert red.num_reductions == 1
+    flat = next(iter(red.groups.values())).flat
+    for b in red.buckets:
+        for p, ptr in zip(b.params, b.ptrs):
+            assert p.grad.data_ptr() == ptr  # grads live in the fusion buffer now
+    want = [p.grad.clone() for p in ddp.parameters()]
+    # accumulate in place into the views (no zero_grad): values double, still the same memory
+    ddp(x).sum().backward()
+    assert all(torch.allclose(p.grad, 2 * w) for p, w in zip(ddp.parameters(), want)) and red.num_reductions == 2
+    assert flat.abs().sum() > 0
+    # forward under no_sync, backward outside: NOT reduced
+    with ddp.no_sync():
+        out = ddp(x)
+    out.sum().backward()
+    assert red.num_reductions == 2
+    # reducer.prepare_for_backward re-arms (what Accelerator.trigger_sync_in_backward reaches into)
+    with ddp.no_sync():
+        out = ddp(x)
+    red.prepare_for_backward([])
+    out.sum().backward()
+    assert red.num_reductions == 3
+    # eval / no_grad forwards never arm
+    with torch.no_grad():
+        ddp(x)
+    assert red._armed is False
+    red.remove_hooks()
+
+
+def test_unused_parameters_policy():
+    class Two(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a, self.b = torch.nn.Linear(2, 2), torch.nn.Linear(2, 2)
+
+        def forward(self, x, use_b=False):
+            return self.b(x) if use_b else self.a(x)
+
+    strict = B200DataParallel(Two())
+    with pytest.raises(RuntimeError, match="did not receive a gradient"):
+        strict(torch.randn(3, 2)).sum().backward()
+    strict.reducer.remove_hooks()
+    lenient = B200DataParallel(Two(), find_unused_parameters=True)
+    lenient(torch.randn(3, 2)).sum().backward()
+    assert lenient.module.b.weight.grad is not None and float(lenient.module.b.weight.grad.abs().sum()) == 0.0
+
+
+def test_comm_hook_registration_surface():
+    from accelerate_b200 import DDPCommunicationHookType, DistributedDataParallelKwargs
+
+    ddp = B200DataParallel(small_model())
+    DistributedDataParallelKwargs(comm_hook=DDPCommunicationHookType.BF16).register_comm_hook(ddp)
+    assert ddp.reducer.wire_dtype == torch.bfloat16
+    ddp(torch.randn(4, 5)).sum().backward()
+    full = B200DataParallel(small_model())
+    full(torch.randn(4, 5)).sum().backward()  # different input: only check representability
+    for p in ddp.parameters():
+        assert torch.equal(p.grad, p.grad.to(torch.bfloat16).float()), "wire format must round gradients to bf16"
+    with pytest.raises(NotImplementedError):
+        DistributedDataParallelKwargs(comm_hook=DDPCommunicationHookType.POWER_SGD).register_comm_hook(ddp)
+    with pytest.raises(NotImplementedError):
+        ddp.register_comm_hook(None, lambda state, bucket: None)
