@@ -247,7 +247,7 @@ class GradReducer:
                 return  # same parameter fired twice in one backward (retain_graph replays): count once
             seen[i] = True
             g = param.grad
-            if g is not None and g.data_ptr() != ptr:
+            if g is not view and g is not None and g.data_ptr() != ptr:
                 # autograd put this gradient somewhere else: adopt it into the fusion buffer
                 bucket.staged.append((i, g if g.is_contiguous() else g.contiguous()))
                 param.grad = view
@@ -574,6 +574,9 @@ class B200DataParallel(torch.nn.Module):
             first = self.bucket_bytes_cap
         self.reducer = GradReducer(self, params, device, world, rank, self.bucket_bytes_cap, first,
                                    find_unused_parameters, process_group)  # fmt: skip
+        # buffer list is fixed at wrap time, like torch DDP's `modules_buffers` (walking ~600 modules every
+        # forward costs ~0.5 ms of host time in a launch-bound step)
+        self._ddp_buffers = [b for b in module.buffers() if b is not None]
         # rank 0's weights (and buffers) become everyone's (torch: _sync_module_states)
         self.reducer.broadcast_parameters(params)
         self._sync_buffers()
@@ -604,7 +607,7 @@ class B200DataParallel(torch.nn.Module):
         )
 
     def _sync_buffers(self):
-        bufs = [b for b in self.module.buffers() if b is not None]
+        bufs = self._ddp_buffers
         if not bufs or self.reducer.world == 1:
             return
         from .utils.operations import broadcast
@@ -619,7 +622,7 @@ class B200DataParallel(torch.nn.Module):
             dev = torch.device(self.reducer.device.type, self.device_ids[0])
             inputs = send_to_device(inputs, dev)
             kwargs = send_to_device(kwargs, dev)
-        if self.broadcast_buffers and self.require_forward_param_sync and self.training:
+        if self._ddp_buffers and self.broadcast_buffers and self.require_forward_param_sync and self.training:
             self._sync_buffers()
         if torch.is_grad_enabled() and self.require_backward_grad_sync:
             self.reducer.prepare_for_backward([])  # latched at forward time, as in torch
