@@ -27,3 +27,9 @@ def test_training_matches_single_process(world):
 def test_local_sgd_cpu():
     out = run_distributed("dist_local_sgd.py", 2, "--device", "cpu", timeout=600)
     assert out.count("LOCAL_SGD_OK") == 2, out[-3000:]
+
+
+def test_bert_accumulation_clip_buffers_cpu():
+    """BASELINE.json config 4 shape (scaled down): bf16, gradient_accumulation_steps=4, clip on the sync step, buffers."""
+    out = run_distributed("dist_bert.py", 2, "--device", "cpu", timeout=600)
+    assert out.count("BERT_CHECK_OK") == 2, out[-3000:]

@@ -45,3 +45,9 @@ def test_local_sgd_two_ranks():
     """LocalSGD parameter averaging through the fusion buffer (pack, one allreduce, unpack, divide)."""
     out = run_distributed("dist_local_sgd.py", 2, "--device", "cuda", env=ENV, timeout=900)
     assert out.count("LOCAL_SGD_OK") == 2, out[-3000:]
+
+
+def test_bert_large_shaped_accumulation_and_clip_two_ranks():
+    """BASELINE.json config 4: BERT-large-shaped seq-cls (1024/16/4096), bf16, accumulate(4) + fused clip + buffer broadcast."""
+    out = run_distributed("dist_bert.py", 2, "--device", "cuda", env=ENV, timeout=1200)
+    assert out.count("BERT_CHECK_OK") == 2, out[-3000:]
