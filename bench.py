@@ -374,7 +374,11 @@ def kernel_roofline(acc, model, rt, world, peaks, peak_src):
         achieved = 2 * nbytes / (t_scale * 1e-3) / 1e9
         peak = float(peaks["hbm_gbs"])
         roof = {"kernel": "multi_scale_kernel<float>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})", "traffic": None,
+                "frac": achieved / peak, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})",
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload, one `ncu --set full`
+                # capture (profiles/r01_n1_clip_kernels_ncu.txt): 1.419 GB + 1.360 GB -> no re-reads
+                "traffic": 2_779_191_000 if nbytes == GRAD_BYTES else None,
+                "traffic_source": "profiles/r01_n1_clip_kernels_ncu.txt",
                 "bytes_per_launch": 2 * nbytes, "ms_per_launch": t_scale}  # fmt: skip
         extra["roofline_stats_kernel"] = {"kernel": "multi_stats_kernel<float>", "bound": "hbm",
                                           "achieved": nbytes / (t_stats * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
@@ -450,6 +454,23 @@ def kernel_roofline(acc, model, rt, world, peaks, peak_src):
                    f"closing barrier replaced by one fence), {blocks} CTAs; time per bucket, max over ranks; bus bandwidth = "
                    "S*2(N-1)/N/t (nccl-tests convention; NVLS moves ~S per GPU so it can exceed the link rate)"}  # fmt: skip
     extra["allreduce_sizes"] = sizes
+    try:  # HBM-side kernel of the fused clip at N > 1: one multiply pass over the fusion buffer (2*S bytes)
+        mult = torch.tensor([0.999], device=dev)
+        n_el = group.total_elems
+        for _ in range(3):
+            rt.ctx.scale_flat(group.flat.data_ptr(), n_el, native.F32, mult.data_ptr(), 0, st)
+        for i in range(reps):
+            ev[2 * i].record()
+            rt.ctx.scale_flat(group.flat.data_ptr(), n_el, native.F32, mult.data_ptr(), 0, st)
+            ev[2 * i + 1].record()
+        torch.cuda.synchronize()
+        t_scale = sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(reps)) / reps
+        hbm = 2 * n_el * 4 / (t_scale * 1e-3) / 1e9
+        extra["roofline_hbm"] = {"kernel": "scale_flat_kernel<float>", "bound": "hbm", "achieved": hbm, "peak": float(peaks["hbm_gbs"]),
+                                 "unit": "GB/s", "frac": hbm / float(peaks["hbm_gbs"]), "bytes_per_launch": 2 * n_el * 4,
+                                 "ms_per_launch": t_scale, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})"}  # fmt: skip
+    except Exception as err:  # never let an auxiliary measurement take the headline down
+        extra["roofline_hbm"] = {"error": str(err)}
     return roof, extra
 
 
