@@ -365,6 +365,9 @@ class GradReducer:
             if self._next < len(self.buckets):
                 self._handle_unready()
             if self.is_cuda:
+                # a device-side flag wait that timed out (dead or diverged peer) latches a status word in mapped
+                # host memory; surface it here instead of training on with unreduced gradients
+                self.rt.ctx.check_status()
                 if self._comm_dirty:
                     # bucket kernels skip their closing barrier; ONE fence per backward proves that every
                     # peer's stores into this rank's fusion buffer (and statistics records) have landed

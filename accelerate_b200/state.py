@@ -141,6 +141,8 @@ class PartialState(_Borg):
 
     # ---- synchronisation (stays on torch.distributed: north star keeps NCCL for init/barrier) ----
     def wait_for_everyone(self):
+        if self.runtime is not None:
+            self.runtime.ctx.check_status()  # surfaces a latched device-side timeout at every barrier point
         if self.use_distributed:
             if self.backend == "nccl":
                 dist.barrier(device_ids=[self.device.index])
