@@ -29,10 +29,6 @@ def is_initialized() -> bool:
     return AcceleratorState._shared != {}
 
 
-def _do_nothing(*args, **kwargs):
-    return None
-
-
 class _Borg:
     """Instances of a subclass all alias one dict; ``_reset_state`` empties it."""
 

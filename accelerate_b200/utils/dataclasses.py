@@ -72,13 +72,6 @@ class RNGType(BaseEnum):
     GENERATOR = "generator"
 
 
-class GradientSyncMode(BaseEnum):
-    """How clip_grad_norm_ consumed the reduction statistics (introspection / tests)."""
-
-    FUSED = "fused"
-    MULTI_TENSOR = "multi_tensor"
-
-
 @dataclass
 class AutocastKwargs(KwargsHandler):
     enabled: bool = True
