@@ -468,12 +468,30 @@ class Accelerator:
                 self._mark_unscaled(red, out)
             else:
                 self.unscale_gradients()
-                out = red.fused_clip_(float(max_norm), norm_type, scale=self.scaler._scale if red.unscaled else None)
+                out = red.fused_clip_(float(max_norm), norm_type, scale=self.scaler._scale if red.unscaled else None,
+                                      defer=self._can_defer_clip(red))
             self.last_clip_mode = "fused"
             return out[0]
         self.unscale_gradients()
         self.last_clip_mode = "multi_tensor"
         return self._multi_tensor_clip(params, float(max_norm), norm_type)
+
+    def _can_defer_clip(self, red) -> bool:
+        """B200DP_DEFER_CLIP=1 and every optimizer owning these gradients will run the fused Adam step."""
+        if os.environ.get("B200DP_DEFER_CLIP", "0") != "1" or self.scaler is not None:
+            return False
+        owners = [o for o in self._optimizers if {id(p) for g in o.param_groups for p in g["params"]} & red._managed_ids]
+        if len(owners) != 1:  # the pending multiplier is handed over exactly once
+            return False
+        for o in owners:
+            if not o._fused_plan_tried:
+                o._fused_plan_tried = True
+                from .optimizer import FusedAdamPlan
+
+                o._fused_plan = FusedAdamPlan.try_build(o.optimizer)
+            if o._fused_plan is None or o._fused_plan.reducer is not red:
+                return False
+        return True
 
     def _scaler_pending(self, red) -> bool:
         """True when every optimizer holding this reducer's parameters still has scaled gradients."""

@@ -968,6 +968,49 @@ extern "C" int b200dp_multi_scale(b200dp_ctx* c, void* const* ptrs, const size_t
 }
 
 // ------------------------------------------------------------------------------------------------
+// K9
+// ------------------------------------------------------------------------------------------------
+extern "C" int b200dp_multi_adam(b200dp_ctx* c, void* const* params, const size_t* numels, const size_t* offs, int n,
+                                 const void* grads, void* exp_avg, void* exp_avg_sq, float decay_mul, float l2,
+                                 float beta1, float beta2, float neg_step_size, float bc2_sqrt, float eps,
+                                 const float* mult_ptr, const float* found_inf_ptr, void* stream) {
+  if (!c || (n > 0 && (!params || !numels || !offs)) || !grads || !exp_avg || !exp_avg_sq)
+    return fail(B200DP_EINVAL, "null argument");
+  DeviceGuard g(c->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  AdamHyper h;
+  h.decay_mul = decay_mul;
+  h.l2 = l2;
+  h.lerp_w = 1.0f - beta1;
+  h.beta2 = beta2;
+  h.one_minus_beta2 = 1.0f - beta2;
+  h.neg_step_size = neg_step_size;
+  h.bc2_sqrt = bc2_sqrt;
+  h.eps = eps;
+  static thread_local AdamTable t;
+  for (int lo = 0; lo < n; lo += kMTMax) {
+    const int cnt = (n - lo) < kMTMax ? (n - lo) : kMTMax;
+    uint32_t acc = 0;
+    for (int i = 0; i < cnt; ++i) {
+      t.param[i] = reinterpret_cast<float*>(params[lo + i]);
+      t.numel[i] = numels[lo + i];
+      t.off[i] = offs[lo + i];
+      t.chunk_start[i] = acc;
+      acc += uint32_t((numels[lo + i] + kMTChunk - 1) / kMTChunk);
+    }
+    t.chunk_start[cnt] = acc;
+    t.n = cnt;
+    if (acc == 0) continue;
+    const int grid = int(acc) < c->sm_count * 8 ? int(acc) : c->sm_count * 8;
+    multi_adam_kernel<<<grid, kStreamThreads, 0, st>>>(t, reinterpret_cast<const float*>(grads),
+                                                        reinterpret_cast<float*>(exp_avg),
+                                                        reinterpret_cast<float*>(exp_avg_sq), h, mult_ptr, found_inf_ptr);
+    KERNEL_OK(c);
+  }
+  return B200DP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // K4
 // ------------------------------------------------------------------------------------------------
 static void pack_push(PackTable* t, int* n, uint32_t* acc, const char* s, char* d, size_t bytes) {

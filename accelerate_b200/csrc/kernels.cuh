@@ -706,6 +706,85 @@ __global__ void __launch_bounds__(kStreamThreads) multi_scale_kernel(const __gri
 }
 
 // ------------------------------------------------------------------------------------------------
+// K9: fused optimizer consumption: one pass Adam/AdamW over fp32 parameters whose
+// gradients and moments live in flat buffers with the fusion-buffer layout.  Arithmetic follows torch's
+// foreach implementation (torch/optim/adam.py `_multi_tensor_adam`, non-capturable branch) operation by
+// operation in float32: decoupled decay `p *= 1 - lr*wd` (AdamW) or `g += wd*p` (Adam), `m.lerp_(g, 1-b1)`,
+// `v = v*b2 + (1-b2)*g*g`, `denom = sqrt(v)/sqrt(1-b2^t) + eps`, `p += (-lr/(1-b1^t)) * (m/denom)`.
+// The clip / unscale multiplier and the found-inf flag are read from device memory, so the separate
+// multiply pass over the gradients disappears and an overflowed step is skipped without a host sync.
+// ------------------------------------------------------------------------------------------------
+struct AdamTable {
+  float* param[kMTMax];
+  unsigned long long numel[kMTMax];
+  unsigned long long off[kMTMax];    // element offset of this parameter in the flat grad / moment buffers
+  uint32_t chunk_start[kMTMax + 1];  // prefix sum of ceil(numel / kMTChunk)
+  int n;
+};
+struct AdamHyper {
+  float decay_mul;      // AdamW: 1 - lr*wd (1 = no decay)
+  float l2;             // Adam: wd added to the gradient (0 = none)
+  float lerp_w;         // 1 - beta1
+  float beta2, one_minus_beta2;
+  float neg_step_size;  // -lr / (1 - beta1^t)
+  float bc2_sqrt;       // sqrt(1 - beta2^t)
+  float eps;
+};
+
+__device__ __forceinline__ void adam_update(float& p, float g, float& m, float& v, const AdamHyper& h, float mult) {
+  g = __fmul_rn(g, mult);
+  if (h.decay_mul != 1.0f) p = __fmul_rn(p, h.decay_mul);
+  if (h.l2 != 0.0f) g = __fadd_rn(g, __fmul_rn(h.l2, p));
+  const float diff = __fsub_rn(g, m);  // torch lerp: |w| < 0.5 ? start + w*diff : end - diff*(1-w)
+  m = (fabsf(h.lerp_w) < 0.5f) ? __fadd_rn(m, __fmul_rn(h.lerp_w, diff)) : __fsub_rn(g, __fmul_rn(diff, 1.0f - h.lerp_w));
+  v = __fmul_rn(v, h.beta2);
+  v = __fadd_rn(v, __fmul_rn(__fmul_rn(h.one_minus_beta2, g), g));
+  const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), h.bc2_sqrt), h.eps);
+  p = __fadd_rn(p, __fmul_rn(h.neg_step_size, __fdiv_rn(m, denom)));
+}
+
+__global__ void __launch_bounds__(kStreamThreads) multi_adam_kernel(const __grid_constant__ AdamTable t,
+                                                                    const float* __restrict__ grads,
+                                                                    float* __restrict__ exp_avg,
+                                                                    float* __restrict__ exp_avg_sq, const AdamHyper h,
+                                                                    const float* __restrict__ mult_ptr,
+                                                                    const float* __restrict__ found_inf_ptr) {
+  if (found_inf_ptr != nullptr && *found_inf_ptr != 0.0f) return;  // overflow: the whole step is skipped
+  const float mult = mult_ptr != nullptr ? *mult_ptr : 1.0f;
+  const uint32_t total = t.chunk_start[t.n];
+  for (uint32_t c = blockIdx.x; c < total; c += gridDim.x) {
+    const int ti = find_tensor(t.chunk_start, t.n, c);
+    const size_t lo = size_t(c - t.chunk_start[ti]) * kMTChunk;
+    const size_t rem = t.numel[ti] - lo;
+    const size_t n = rem < size_t(kMTChunk) ? rem : size_t(kMTChunk);
+    float* p = t.param[ti] + lo;
+    const float* g = grads + t.off[ti] + lo;
+    float* m = exp_avg + t.off[ti] + lo;
+    float* v = exp_avg_sq + t.off[ti] + lo;
+    const uintptr_t al = reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                         reinterpret_cast<uintptr_t>(v);
+    size_t done = 0;
+    if ((al & 15) == 0) {
+      const size_t nvec = n >> 2;
+      for (size_t i = threadIdx.x; i < nvec; i += blockDim.x) {
+        float fp[4], fg[4], fm[4], fv[4];
+        Vec16<float>::unpack(ld_stream16(p + i * 4), fp);
+        Vec16<float>::unpack(ld_stream16(g + i * 4), fg);
+        Vec16<float>::unpack(ld_stream16(m + i * 4), fm);
+        Vec16<float>::unpack(ld_stream16(v + i * 4), fv);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) adam_update(fp[k], fg[k], fm[k], fv[k], h, mult);
+        st_stream16(p + i * 4, Vec16<float>::pack(fp));
+        st_stream16(m + i * 4, Vec16<float>::pack(fm));
+        st_stream16(v + i * 4, Vec16<float>::pack(fv));
+      }
+      done = nvec << 2;
+    }
+    for (size_t i = done + threadIdx.x; i < n; i += blockDim.x) adam_update(p[i], g[i], m[i], v[i], h, mult);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K6: norm finalisation + flat scale / clamp.
 // ------------------------------------------------------------------------------------------------
 // total over records [slot0, slot0+nslots) x ranks; every rank sums the same records in the same

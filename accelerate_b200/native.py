@@ -44,7 +44,7 @@ EXPORTS = [
     "b200dp_mc_attach", "b200dp_mc_bind", "b200dp_seg_mc_ptr", "b200dp_control_bytes",
     "b200dp_set_control", "b200dp_fdx_open", "b200dp_fdx_send", "b200dp_fdx_recv", "b200dp_fdx_close",
     "b200dp_stream_wait", "b200dp_fence", "b200dp_allreduce_bucket", "b200dp_allreduce_oneshot", "b200dp_finalize_norm",
-    "b200dp_scale_flat", "b200dp_clamp_flat", "b200dp_cast", "b200dp_multi_stats", "b200dp_multi_scale", "b200dp_pack",
+    "b200dp_scale_flat", "b200dp_clamp_flat", "b200dp_cast", "b200dp_multi_stats", "b200dp_multi_scale", "b200dp_multi_adam", "b200dp_pack",
     "b200dp_pull", "b200dp_push_max_bytes", "b200dp_push_area_bytes", "b200dp_push", "b200dp_exchange_small",
     "b200dp_pad_copy",
 ]  # fmt: skip
@@ -155,6 +155,8 @@ def load():
             "b200dp_cast": [vp, vp, i, vp, i, sz, c_float, i, vp],
             "b200dp_multi_stats": [vp, POINTER(vp), POINTER(sz), i, i, i, vp],
             "b200dp_multi_scale": [vp, POINTER(vp), POINTER(sz), i, i, vp, vp],
+            "b200dp_multi_adam": [vp, POINTER(vp), POINTER(sz), POINTER(sz), i, vp, vp, vp, c_float, c_float, c_float, c_float,
+                                  c_float, c_float, c_float, vp, vp, vp],
             "b200dp_pack": [vp, POINTER(vp), POINTER(vp), POINTER(sz), i, i, vp],
             "b200dp_pull": [vp, i, sz, sz, vp, sz, i, i, i, i, vp],
             "b200dp_push": [vp, i, i, vp, sz, i, c_double, vp, i, vp],
@@ -336,6 +338,21 @@ class Context:
         pa = (c_void_p * n)(*ptrs)
         na = (c_size_t * n)(*numels)
         _check(self.lib, self.lib.b200dp_multi_scale(self.h, pa, na, n, dtype, mult_ptr, stream), "b200dp_multi_scale")
+
+    def make_adam_table(self, params, numels, offs):
+        """ctypes arrays for multi_adam, built once per parameter group (pointers are stable)."""
+        n = len(params)
+        return (c_void_p * n)(*params), (c_size_t * n)(*numels), (c_size_t * n)(*offs), n
+
+    def multi_adam(self, table, grads, exp_avg, exp_avg_sq, decay_mul, l2, beta1, beta2, neg_step_size, bc2_sqrt, eps,
+                   mult_ptr, found_inf_ptr, stream):  # fmt: skip
+        pa, na, oa, n = table
+        _check(
+            self.lib,
+            self.lib.b200dp_multi_adam(self.h, pa, na, oa, n, grads, exp_avg, exp_avg_sq, decay_mul, l2, beta1, beta2,
+                                       neg_step_size, bc2_sqrt, eps, mult_ptr, found_inf_ptr, stream),
+            "b200dp_multi_adam",
+        )  # fmt: skip
 
     def pack(self, srcs, dsts, nbytes, use_bulk, stream):
         n = len(srcs)

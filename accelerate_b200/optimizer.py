@@ -10,6 +10,7 @@ kernel's statistics rather than from a separate pass over the gradients.
 from __future__ import annotations
 
 import inspect
+import os
 
 import torch
 
@@ -26,6 +27,99 @@ def _to_device(obj, device):
     return obj
 
 
+class FusedAdamPlan:
+    """Fused optimizer consumption, opt-in with ``B200DP_FUSED_ADAM=1``.
+
+    When the wrapped optimizer is a plain ``torch.optim.Adam`` / ``AdamW`` over fp32 parameters whose
+    gradients are views of one reducer's fusion buffer, its ~10 foreach launches are replaced by ONE
+    multi-tensor kernel (``b200dp_multi_adam``) that reads p, g, m, v and writes p, m, v — and, with
+    ``B200DP_DEFER_CLIP=1``, applies the pending clip / unscale multiplier on the fly so the separate
+    multiply pass over the gradients disappears.  The optimizer object stays the user's: ``param_groups``
+    (schedulers), ``state`` (``step`` / ``exp_avg`` / ``exp_avg_sq``, now views of two flat buffers) and
+    ``state_dict()`` keep their torch layout, and any step that is not eligible falls through to
+    ``optimizer.step()`` on that very state.
+    """
+
+    def __init__(self, optimizer, reducer, group):
+        self.optimizer, self.reducer, self.group = optimizer, reducer, group
+        self.decoupled_default = isinstance(optimizer, torch.optim.AdamW)
+        where = {}
+        for b in reducer.buckets:
+            if b.group is group:
+                for p, off, n in zip(b.params, b.offsets, b.numels):
+                    where[id(p)] = (off, n)
+        self.m_flat = torch.zeros(group.total_elems, dtype=torch.float32, device=reducer.device)
+        self.v_flat = torch.zeros(group.total_elems, dtype=torch.float32, device=reducer.device)
+        self.tables = []
+        ctx = reducer.rt.ctx
+        for pg in optimizer.param_groups:
+            params = [p for p in pg["params"] if p.requires_grad]
+            ptrs, numels, offs = [], [], []
+            for p in params:
+                off, n = where[id(p)]
+                st = optimizer.state[p]
+                m_view = self.m_flat[off : off + n].view(p.shape)
+                v_view = self.v_flat[off : off + n].view(p.shape)
+                if "exp_avg" in st:  # resumed run: adopt the existing moments
+                    m_view.copy_(st["exp_avg"])
+                    v_view.copy_(st["exp_avg_sq"])
+                st["exp_avg"], st["exp_avg_sq"] = m_view, v_view
+                if "step" not in st:
+                    st["step"] = torch.tensor(0.0, dtype=torch.float32)
+                ptrs.append(p.data_ptr())
+                numels.append(n)
+                offs.append(off)
+            self.tables.append((params, ctx.make_adam_table(ptrs, numels, offs)))
+
+    @staticmethod
+    def try_build(optimizer):
+        if os.environ.get("B200DP_FUSED_ADAM", "0") != "1" or type(optimizer) not in (torch.optim.Adam, torch.optim.AdamW):
+            return None
+        from .reducer import live_reducers
+
+        wanted = [p for pg in optimizer.param_groups for p in pg["params"] if p.requires_grad]
+        if not wanted or any(p.dtype != torch.float32 or not p.is_cuda or not p.is_contiguous() for p in wanted):
+            return None
+        for pg in optimizer.param_groups:
+            if pg.get("amsgrad") or pg.get("maximize") or pg.get("capturable") or pg.get("differentiable") or pg.get("fused"):
+                return None
+            if isinstance(pg["lr"], torch.Tensor) or any(isinstance(b, torch.Tensor) for b in pg["betas"]):
+                return None
+        ids = {id(p) for p in wanted}
+        for red in live_reducers():
+            if red.is_cuda and ids <= red._managed_ids and torch.float32 in red.groups:
+                return FusedAdamPlan(optimizer, red, red.groups[torch.float32])
+        return None
+
+    def step(self) -> bool:
+        """Run the fused update; False = not applicable right now (caller falls back to optimizer.step())."""
+        red = self.reducer
+        if not red.grads_in_buffer():
+            return False
+        ctx = red.rt.ctx
+        stream = torch.cuda.current_stream(red.device).cuda_stream
+        pending = red.take_pending_multiplier()
+        mult_ptr = pending.data_ptr() + 4 if pending is not None else None
+        found_ptr = None  # without a GradScaler torch applies the update even to non-finite gradients: keep that
+        for pg, (params, table) in zip(self.optimizer.param_groups, self.tables):
+            if not params:
+                continue
+            steps = [self.optimizer.state[p]["step"] for p in params]
+            torch._foreach_add_(steps, 1)
+            t = float(steps[0])
+            lr, (beta1, beta2), eps, wd = float(pg["lr"]), pg["betas"], float(pg["eps"]), float(pg["weight_decay"])
+            decoupled = pg.get("decoupled_weight_decay", self.decoupled_default)
+            decay_mul = (1 - lr * wd) if (decoupled and wd != 0) else 1.0
+            l2 = wd if (not decoupled and wd != 0) else 0.0
+            bc1 = 1 - beta1**t
+            bc2_sqrt = (1 - beta2**t) ** 0.5
+            ctx.multi_adam(table, self.group.flat.data_ptr(), self.m_flat.data_ptr(), self.v_flat.data_ptr(), decay_mul, l2,
+                           beta1, beta2, -(lr / bc1), bc2_sqrt, eps, mult_ptr, found_ptr, stream)  # fmt: skip
+        if pending is not None:
+            self._keepalive = pending  # the kernels read it asynchronously
+        return True
+
+
 class AcceleratedOptimizer(torch.optim.Optimizer):
     def __init__(self, optimizer, device_placement: bool = True, scaler=None):
         self.optimizer = optimizer
@@ -35,6 +129,8 @@ class AcceleratedOptimizer(torch.optim.Optimizer):
         self.device_placement = device_placement
         self._is_overflow = False
         self._stepped = False  # set by the instrumented inner step
+        self._fused_plan = None  # built lazily at the first step (parameters must be wrapped by then)
+        self._fused_plan_tried = False
         if scaler is not None:
             self._arm_step_probe()
         if device_placement:
@@ -108,6 +204,8 @@ class AcceleratedOptimizer(torch.optim.Optimizer):
         if not self.gradient_state.sync_gradients:
             return
         if self.scaler is None:
+            if closure is None and self._fused_step():
+                return
             self.optimizer.step(closure)
             return
         self._stepped = False
@@ -119,6 +217,13 @@ class AcceleratedOptimizer(torch.optim.Optimizer):
             self.optimizer.step = self._inner_step
         self._is_overflow = not self._stepped
 
+    def _fused_step(self) -> bool:
+        if not self._fused_plan_tried:
+            self._fused_plan_tried = True
+            if self.accelerator_state.device.type == "cuda":
+                self._fused_plan = FusedAdamPlan.try_build(self.optimizer)
+        return self._fused_plan is not None and self._fused_plan.step()
+
     @property
     def step_was_skipped(self) -> bool:
         return self._is_overflow
@@ -128,7 +233,7 @@ class AcceleratedOptimizer(torch.optim.Optimizer):
             group["params"] = [parameters_map.get(p, p) for p in group["params"]]
 
     def __getstate__(self):
-        drop = {"_inner_step", "_probed_step"}
+        drop = {"_inner_step", "_probed_step", "_fused_plan"}
         return {k: v for k, v in self.__dict__.items() if k not in drop}
 
     def __setstate__(self, state):

@@ -155,6 +155,7 @@ class GradReducer:
         self._graveyard = []
         self._comm_dirty = False
         self._wire_dirty = False
+        self._pending_mult = None
         self.rt = None
         if self.is_cuda:
             from .runtime import SymmRuntime, native_dtype
@@ -419,6 +420,7 @@ class GradReducer:
         """Arm the next backward (torch Reducer::prepare_for_backward; reached from accelerator.py:1222)."""
         self._armed = True
         self.stats_valid = False
+        self._pending_mult = None  # a deferred clip that no optimizer step consumed dies with its gradients
         if self.is_cuda:
             self.compute_stream = torch.cuda.current_stream(self.device).cuda_stream
         self._reset_iteration()
@@ -445,7 +447,7 @@ class GradReducer:
         ids = {id(p) for p in parameters if p.grad is not None}
         return ids == self._managed_ids and self.grads_in_buffer()
 
-    def fused_clip_(self, max_norm: float, norm_type: float = 2.0, scale: torch.Tensor | None = None):
+    def fused_clip_(self, max_norm: float, norm_type: float = 2.0, scale: torch.Tensor | None = None, defer: bool = False):
         """clip_grad_norm_ and/or GradScaler.unscale_ from the statistics the allreduce kernels already
         produced: one 1-CTA finalize + one multiply pass over the fusion buffer that exits at once
         when the multiplier is 1.  Returns a 3-float device tensor ``[total_norm, multiplier,
@@ -467,13 +469,23 @@ class GradReducer:
             # gradients already carry 1/S: keep only the clip coefficient (exact for power-of-two S)
             out[1].mul_(scale.to(torch.float32).reshape(()))
         mult_ptr = out.data_ptr() + 4
-        for group in self.groups.values():
-            ctx.scale_flat(group.flat.data_ptr(), group.total_elems, group.native_dtype, mult_ptr, 0, st)
+        if defer and scale is None:
+            # fused optimizer consumption: the Adam kernel multiplies on the fly; p.grad keeps the UNCLIPPED values
+            self._pending_mult = out
+        else:
+            for group in self.groups.values():
+                ctx.scale_flat(group.flat.data_ptr(), group.total_elems, group.native_dtype, mult_ptr, 0, st)
         if scale is not None:
             self.unscaled = True
         if max_norm >= 0:
             self.stats_valid = False  # the buffer no longer holds the values the statistics describe
         return out
+
+    def take_pending_multiplier(self):
+        """The [total_norm, multiplier, found_inf] tensor of a deferred clip (B200DP_DEFER_CLIP=1), handed to the
+        fused optimizer step exactly once."""
+        pending, self._pending_mult = self._pending_mult, None
+        return pending
 
     def clamp_(self, clip_value: float):
         st = torch.cuda.current_stream(self.device).cuda_stream

@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--model", default=os.environ.get("BENCH_MODEL", "gpt2-medium"))
     ap.add_argument("--no-ddp-leg", action="store_true", help="skip the stock torch DDP+NCCL comparison leg")
     ap.add_argument("--no-cpu-leg", action="store_true")
+    ap.add_argument("--fused-adam", action="store_true", help="opt-in: SURVEY 8f row 1, fused AdamW + deferred clip (A/B only)")
     return ap.parse_args()
 
 
@@ -220,6 +221,9 @@ def main():
     from accelerate_b200.state import PartialState
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback for the product path)"
+    if args.fused_adam:
+        os.environ["B200DP_FUSED_ADAM"] = "1"
+        os.environ["B200DP_DEFER_CLIP"] = "1"
     acc = Accelerator(mixed_precision="bf16", kwargs_handlers=[DistributedDataParallelKwargs(bucket_cap_mb=25)])
     rank, world, dev = acc.process_index, acc.num_processes, acc.device
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE is {world}: launch with torchrun --nproc-per-node {args.gpus}"
@@ -315,7 +319,7 @@ def main():
                             "+ clip_grad_norm_(1.0) + AdamW + zero_grad",
                 "global_batch": gb, "per_gpu_batch": B, "seq_len": SEQ, "parallelism": f"dp{world}", "bucket_cap_mb": 25,
                 "l2": "per-step working set (1.4 GB grads + weights + activations) exceeds the 126 MB L2; no flush needed",
-                "clip_mode": clip_mode, "final_loss": float(last_loss.detach()),
+                "clip_mode": clip_mode, "final_loss": float(last_loss.detach()), "fused_adam": bool(args.fused_adam),
             },
             "e2e": {"value": gb * steps / (e2e_ms / 1e3), "unit": "samples/s", "h2d_bytes_per_step": B * SEQ * 8,
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / steps},

@@ -193,6 +193,21 @@ int b200dp_multi_stats(b200dp_ctx* ctx, const void* const* ptrs, const size_t* n
 int b200dp_multi_scale(b200dp_ctx* ctx, void* const* ptrs, const size_t* numels, int n, int dtype,
                        const float* mult_ptr, void* stream);
 
+/* ---- K9: fused optimizer consumption -------------------------------------
+ * Replaces: the ~10 foreach launches of torch.optim.Adam/AdamW.step that AcceleratedOptimizer.step reaches
+ * (src/accelerate/optimizer.py:145-181) plus the clip multiply pass, for fp32 parameters whose gradients and
+ * moments live in flat buffers laid out like the fusion buffer: one pass reads p, g, m, v and writes p, m, v.
+ * params[i] has numels[i] elements; its gradient / moments start at element offs[i] of grads / exp_avg /
+ * exp_avg_sq.  Hyper-parameters as torch computes them on the host for step t:
+ *   decay_mul = 1 - lr*wd (AdamW; pass 1 for none), l2 = wd (Adam's coupled L2; 0 for none),
+ *   neg_step_size = -lr/(1-beta1^t), bc2_sqrt = sqrt(1-beta2^t).
+ * mult_ptr (device, may be NULL): gradient multiplier (clip coefficient x 1/loss-scale); found_inf_ptr (device,
+ * may be NULL): non-zero skips the whole step. */
+int b200dp_multi_adam(b200dp_ctx* ctx, void* const* params, const size_t* numels, const size_t* offs, int n,
+                      const void* grads, void* exp_avg, void* exp_avg_sq, float decay_mul, float l2, float beta1,
+                      float beta2, float neg_step_size, float bc2_sqrt, float eps, const float* mult_ptr,
+                      const float* found_inf_ptr, void* stream);
+
 /* ---- K4: bucket pack / unpack (multi-tensor copy) -------------------------------------------
  * Replaces: the per-parameter grad->bucket and bucket->grad copy kernels of the Reducer
  * (torch reducer.hpp:276,286,328).  n (src,dst,bytes) triples, one launch.  use_bulk=1 moves

@@ -179,6 +179,32 @@ def bucket_assignment(sizes_bytes, first_cap=1 << 20, cap=25 << 20):
 
 
 # --------------------------------------------------------------------------------------------
+# a8 / §8f row 1: the optimizer step the reduced gradients feed   (reference: optimizer.py:145-181 ->
+# torch/optim/adam.py `_multi_tensor_adam`, non-capturable branch; AdamW = decoupled weight decay)
+# --------------------------------------------------------------------------------------------
+def adam_step(p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, decoupled=True, mult=1.0):
+    """One Adam/AdamW update in float32, operation by operation as torch's foreach implementation does it.
+    ``step`` is the 1-based step count AFTER the increment.  Returns new (p, m, v)."""
+    p, g, m, v = (np.asarray(a, dtype=F32).copy() for a in (p, g, m, v))
+    g = g * F32(mult)
+    if weight_decay != 0:
+        if decoupled:
+            p = p * F32(1 - lr * weight_decay)
+        else:
+            g = g + F32(weight_decay) * p
+    w = F32(1 - beta1)
+    diff = g - m
+    m = m + w * diff if abs(float(w)) < 0.5 else g - diff * (F32(1.0) - w)
+    v = v * F32(beta2)
+    v = v + (F32(1 - beta2) * g) * g
+    bc1 = 1 - beta1**step
+    bc2_sqrt = (1 - beta2**step) ** 0.5
+    denom = np.sqrt(v) / F32(bc2_sqrt) + F32(eps)
+    p = p + F32(-(lr / bc1)) * (m / denom)
+    return p, m, v
+
+
+# --------------------------------------------------------------------------------------------
 # one whole step of the path, for smoke tests and the CPU baseline
 # --------------------------------------------------------------------------------------------
 def reduce_and_clip_step(per_rank_flat_grads, max_norm=1.0):

@@ -173,3 +173,65 @@ def test_fp16_scaler_fused_unscale_clip_and_overflow_skip():
         acc.clip_grad_norm_(ddp.parameters(), 0.05)
     opt.step()
     assert not opt.step_was_skipped
+
+
+@pytest.mark.parametrize("cls", [torch.optim.AdamW, torch.optim.Adam])
+@pytest.mark.parametrize("defer", ["0", "1"])
+def test_fused_adam_consumption_matches_torch(cls, defer, monkeypatch):
+    """SURVEY.md §8f row 1 (opt-in B200DP_FUSED_ADAM=1): one multi-tensor kernel instead of torch's foreach Adam/AdamW,
+    optionally consuming the deferred clip multiplier; parameters and optimizer state must track torch's own
+    optimizer (fp32 rounding) over several steps with a scheduler and two parameter groups."""
+    from accelerate_b200 import Accelerator, B200DataParallel
+    from accelerate_b200.state import PartialState
+
+    monkeypatch.setenv("B200DP_FUSED_ADAM", "1")
+    monkeypatch.setenv("B200DP_DEFER_CLIP", defer)
+    acc = Accelerator()
+    model, ref = mlp(3), mlp(3)
+    ddp = B200DataParallel(model, device_ids=[0], bucket_cap_mb=0.02)
+
+    def groups(m):
+        decay = [p for p in m.parameters() if p.ndim > 1]
+        rest = [p for p in m.parameters() if p.ndim <= 1]
+        return [{"params": decay, "weight_decay": 0.1}, {"params": rest, "weight_decay": 0.0}]
+
+    opt = cls(groups(model), lr=3e-3, betas=(0.9, 0.95))
+    ref_opt = cls(groups(ref), lr=3e-3, betas=(0.9, 0.95), foreach=True)
+    sched = torch.optim.lr_scheduler.StepLR(opt, 1, gamma=0.8)
+    ref_sched = torch.optim.lr_scheduler.StepLR(ref_opt, 1, gamma=0.8)
+    opt, sched = acc.prepare(opt, sched)
+    rt = PartialState().runtime
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for step in range(5):
+        x = torch.randn(8, 64, device="cuda", generator=g)
+        ddp(x).square().mean().backward()
+        ref(x).square().mean().backward()
+        tn = acc.clip_grad_norm_(ddp.parameters(), 0.05)
+        ref_tn = torch.nn.utils.clip_grad_norm_(ref.parameters(), 0.05)
+        assert torch.allclose(tn, ref_tn, rtol=1e-5)
+        launches = rt.ctx.launches
+        opt.step()
+        assert opt._fused_plan is not None and rt.ctx.launches - launches == 2, "one fused launch per parameter group"
+        ref_opt.step()
+        sched.step()
+        ref_sched.step()
+        opt.zero_grad(set_to_none=False)  # grads stay views of the fusion buffer
+        ref_opt.zero_grad()
+        for p, q in zip(model.parameters(), ref.parameters()):
+            assert torch.allclose(p, q, rtol=1e-5, atol=1e-7), step
+    for p, q in zip(model.parameters(), ref.parameters()):
+        a, b = opt.optimizer.state[p], ref_opt.state[q]
+        assert float(a["step"]) == float(b["step"]) == 5.0
+        assert torch.allclose(a["exp_avg"], b["exp_avg"], rtol=1e-5, atol=1e-8)
+        assert torch.allclose(a["exp_avg_sq"], b["exp_avg_sq"], rtol=1e-5, atol=1e-10)
+    # the optimizer is still the user's: state_dict round-trips, and an ineligible step falls back to torch's own
+    sd = opt.state_dict()
+    assert len(sd["state"]) == 4 and sd["param_groups"][0]["lr"] == ref_opt.param_groups[0]["lr"]
+    opt.zero_grad(set_to_none=True)
+    ddp(x).square().mean().backward()
+    for p in model.parameters():
+        p.grad = p.grad.clone()  # no longer views -> plan declines
+    before = rt.ctx.launches
+    opt.step()
+    assert rt.ctx.launches == before, "fallback must not launch the fused kernel"
+    rt.ctx.check_status()

@@ -125,3 +125,24 @@ def test_bucket_assignment_matches_torch():
     for first, cap in [(1 << 20, 25 << 20), (15 << 20, 15 << 20), (1, 1)]:
         want, _ = dist._compute_bucket_assignment_by_size(tensors, [first, cap])
         assert oracle.bucket_assignment(sizes, first, cap) == want
+
+
+@pytest.mark.parametrize("cls,decoupled", [(torch.optim.AdamW, True), (torch.optim.Adam, False)])
+def test_adam_step_matches_torch_foreach(cls, decoupled):
+    """The oracle's optimizer restatement against torch's own foreach Adam/AdamW on CPU, several steps, changing lr."""
+    g = torch.Generator().manual_seed(2)
+    for wd, betas in [(0.01, (0.9, 0.999)), (0.0, (0.9, 0.999)), (0.1, (0.4, 0.95))]:
+        p = torch.nn.Parameter(torch.randn(257, generator=g))
+        opt = cls([p], lr=1e-2, weight_decay=wd, betas=betas, foreach=True)
+        op, om, ov = p.detach().numpy().copy(), np.zeros(257, np.float32), np.zeros(257, np.float32)
+        for step in range(1, 6):
+            lr = 1e-2 * 0.7**step
+            opt.param_groups[0]["lr"] = lr
+            grad = torch.randn(257, generator=g)
+            p.grad = grad.clone()
+            opt.step()
+            op, om, ov = oracle.adam_step(op, grad.numpy(), om, ov, step, lr, betas[0], betas[1], 1e-8, wd, decoupled)
+            assert np.allclose(op, p.detach().numpy(), rtol=1e-5, atol=1e-6), (cls, wd, step)
+            st = opt.state[p]
+            assert np.allclose(om, st["exp_avg"].numpy(), rtol=1e-5, atol=1e-6)
+            assert np.allclose(ov, st["exp_avg_sq"].numpy(), rtol=1e-5, atol=1e-8)
