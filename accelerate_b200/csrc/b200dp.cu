@@ -970,11 +970,11 @@ extern "C" int b200dp_multi_scale(b200dp_ctx* c, void* const* ptrs, const size_t
 // ------------------------------------------------------------------------------------------------
 // K9
 // ------------------------------------------------------------------------------------------------
-extern "C" int b200dp_multi_adam(b200dp_ctx* c, void* const* params, const size_t* numels, const size_t* offs, int n,
-                                 const void* grads, void* exp_avg, void* exp_avg_sq, float decay_mul, float l2,
+extern "C" int b200dp_multi_adam(b200dp_ctx* c, void* const* params, const void* const* grads, const size_t* numels,
+                                 const size_t* offs, int n, void* exp_avg, void* exp_avg_sq, float decay_mul, float l2,
                                  float beta1, float beta2, float neg_step_size, float bc2_sqrt, float eps,
                                  const float* mult_ptr, const float* found_inf_ptr, void* stream) {
-  if (!c || (n > 0 && (!params || !numels || !offs)) || !grads || !exp_avg || !exp_avg_sq)
+  if (!c || (n > 0 && (!params || !grads || !numels || !offs)) || !exp_avg || !exp_avg_sq)
     return fail(B200DP_EINVAL, "null argument");
   DeviceGuard g(c->device);
   cudaStream_t st = (cudaStream_t)stream;
@@ -993,6 +993,7 @@ extern "C" int b200dp_multi_adam(b200dp_ctx* c, void* const* params, const size_
     uint32_t acc = 0;
     for (int i = 0; i < cnt; ++i) {
       t.param[i] = reinterpret_cast<float*>(params[lo + i]);
+      t.grad[i] = reinterpret_cast<const float*>(grads[lo + i]);
       t.numel[i] = numels[lo + i];
       t.off[i] = offs[lo + i];
       t.chunk_start[i] = acc;
@@ -1002,8 +1003,7 @@ extern "C" int b200dp_multi_adam(b200dp_ctx* c, void* const* params, const size_
     t.n = cnt;
     if (acc == 0) continue;
     const int grid = int(acc) < c->sm_count * 8 ? int(acc) : c->sm_count * 8;
-    multi_adam_kernel<<<grid, kStreamThreads, 0, st>>>(t, reinterpret_cast<const float*>(grads),
-                                                        reinterpret_cast<float*>(exp_avg),
+    multi_adam_kernel<<<grid, kStreamThreads, 0, st>>>(t, reinterpret_cast<float*>(exp_avg),
                                                         reinterpret_cast<float*>(exp_avg_sq), h, mult_ptr, found_inf_ptr);
     KERNEL_OK(c);
   }

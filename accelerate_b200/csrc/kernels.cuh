@@ -716,8 +716,9 @@ __global__ void __launch_bounds__(kStreamThreads) multi_scale_kernel(const __gri
 // ------------------------------------------------------------------------------------------------
 struct AdamTable {
   float* param[kMTMax];
+  const float* grad[kMTMax];         // gradient of this parameter (a fusion-buffer view or a loose tensor)
   unsigned long long numel[kMTMax];
-  unsigned long long off[kMTMax];    // element offset of this parameter in the flat grad / moment buffers
+  unsigned long long off[kMTMax];    // element offset of this parameter in the flat moment buffers
   uint32_t chunk_start[kMTMax + 1];  // prefix sum of ceil(numel / kMTChunk)
   int n;
 };
@@ -744,7 +745,6 @@ __device__ __forceinline__ void adam_update(float& p, float g, float& m, float& 
 }
 
 __global__ void __launch_bounds__(kStreamThreads) multi_adam_kernel(const __grid_constant__ AdamTable t,
-                                                                    const float* __restrict__ grads,
                                                                     float* __restrict__ exp_avg,
                                                                     float* __restrict__ exp_avg_sq, const AdamHyper h,
                                                                     const float* __restrict__ mult_ptr,
@@ -758,7 +758,7 @@ __global__ void __launch_bounds__(kStreamThreads) multi_adam_kernel(const __grid
     const size_t rem = t.numel[ti] - lo;
     const size_t n = rem < size_t(kMTChunk) ? rem : size_t(kMTChunk);
     float* p = t.param[ti] + lo;
-    const float* g = grads + t.off[ti] + lo;
+    const float* g = t.grad[ti] + lo;
     float* m = exp_avg + t.off[ti] + lo;
     float* v = exp_avg_sq + t.off[ti] + lo;
     const uintptr_t al = reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |

@@ -155,8 +155,8 @@ def load():
             "b200dp_cast": [vp, vp, i, vp, i, sz, c_float, i, vp],
             "b200dp_multi_stats": [vp, POINTER(vp), POINTER(sz), i, i, i, vp],
             "b200dp_multi_scale": [vp, POINTER(vp), POINTER(sz), i, i, vp, vp],
-            "b200dp_multi_adam": [vp, POINTER(vp), POINTER(sz), POINTER(sz), i, vp, vp, vp, c_float, c_float, c_float, c_float,
-                                  c_float, c_float, c_float, vp, vp, vp],
+            "b200dp_multi_adam": [vp, POINTER(vp), POINTER(vp), POINTER(sz), POINTER(sz), i, vp, vp, c_float, c_float, c_float,
+                                  c_float, c_float, c_float, c_float, vp, vp, vp],
             "b200dp_pack": [vp, POINTER(vp), POINTER(vp), POINTER(sz), i, i, vp],
             "b200dp_pull": [vp, i, sz, sz, vp, sz, i, i, i, i, vp],
             "b200dp_push": [vp, i, i, vp, sz, i, c_double, vp, i, vp],
@@ -339,17 +339,21 @@ class Context:
         na = (c_size_t * n)(*numels)
         _check(self.lib, self.lib.b200dp_multi_scale(self.h, pa, na, n, dtype, mult_ptr, stream), "b200dp_multi_scale")
 
-    def make_adam_table(self, params, numels, offs):
-        """ctypes arrays for multi_adam, built once per parameter group (pointers are stable)."""
+    def make_adam_table(self, params, numels, offs, grads=None):
+        """ctypes arrays for multi_adam.  With ``grads`` (fusion-buffer views: stable pointers) the table is complete
+        and can be cached; without, the gradient pointers are supplied per step."""
         n = len(params)
-        return (c_void_p * n)(*params), (c_size_t * n)(*numels), (c_size_t * n)(*offs), n
+        ga = (c_void_p * n)(*grads) if grads is not None else None
+        return (c_void_p * n)(*params), ga, (c_size_t * n)(*numels), (c_size_t * n)(*offs), n
 
-    def multi_adam(self, table, grads, exp_avg, exp_avg_sq, decay_mul, l2, beta1, beta2, neg_step_size, bc2_sqrt, eps,
-                   mult_ptr, found_inf_ptr, stream):  # fmt: skip
-        pa, na, oa, n = table
+    def multi_adam(self, table, exp_avg, exp_avg_sq, decay_mul, l2, beta1, beta2, neg_step_size, bc2_sqrt, eps,
+                   mult_ptr, found_inf_ptr, stream, grads=None):  # fmt: skip
+        pa, ga, na, oa, n = table
+        if grads is not None:
+            ga = (c_void_p * n)(*grads)
         _check(
             self.lib,
-            self.lib.b200dp_multi_adam(self.h, pa, na, oa, n, grads, exp_avg, exp_avg_sq, decay_mul, l2, beta1, beta2,
+            self.lib.b200dp_multi_adam(self.h, pa, ga, na, oa, n, exp_avg, exp_avg_sq, decay_mul, l2, beta1, beta2,
                                        neg_step_size, bc2_sqrt, eps, mult_ptr, found_inf_ptr, stream),
             "b200dp_multi_adam",
         )  # fmt: skip

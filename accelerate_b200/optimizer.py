@@ -28,57 +28,88 @@ def _to_device(obj, device):
 
 
 class FusedAdamPlan:
-    """Fused optimizer consumption, opt-in with ``B200DP_FUSED_ADAM=1``.
+    """Fused optimizer consumption; ``B200DP_FUSED_ADAM=0`` turns it off.
 
-    When the wrapped optimizer is a plain ``torch.optim.Adam`` / ``AdamW`` over fp32 parameters whose
-    gradients are views of one reducer's fusion buffer, its ~10 foreach launches are replaced by ONE
-    multi-tensor kernel (``b200dp_multi_adam``) that reads p, g, m, v and writes p, m, v — and, with
-    ``B200DP_DEFER_CLIP=1``, applies the pending clip / unscale multiplier on the fly so the separate
-    multiply pass over the gradients disappears.  The optimizer object stays the user's: ``param_groups``
-    (schedulers), ``state`` (``step`` / ``exp_avg`` / ``exp_avg_sq``, now views of two flat buffers) and
-    ``state_dict()`` keep their torch layout, and any step that is not eligible falls through to
-    ``optimizer.step()`` on that very state.
+    When the wrapped optimizer is a plain ``torch.optim.Adam`` / ``AdamW`` over fp32 CUDA parameters, its
+    ~10 foreach launches are replaced by ONE multi-tensor kernel (``b200dp_multi_adam``) that reads p, g, m, v
+    and writes p, m, v.  Two layouts:
+
+    * *buffer* (multi-GPU): the gradients are views of one reducer's fusion buffer; the moments live in two flat
+      buffers with the same layout, the pointer table is built once.  With ``B200DP_DEFER_CLIP=1`` the pending
+      clip / unscale multiplier is applied on the fly, so the separate multiply pass over the gradients disappears.
+    * *loose* (one process, no reducer): the gradients are whatever tensors autograd left in ``param.grad``; their
+      pointers are collected per step, the moments still live in two flat buffers.
+
+    The optimizer object stays the user's: ``param_groups`` (schedulers), ``state`` (``step`` / ``exp_avg`` /
+    ``exp_avg_sq``, now views of the flat buffers) and ``state_dict()`` keep their torch layout, and any step that
+    is not eligible falls through to ``optimizer.step()`` on that very state.
     """
 
-    def __init__(self, optimizer, reducer, group):
-        self.optimizer, self.reducer, self.group = optimizer, reducer, group
+    def __init__(self, optimizer, ctx, device, reducer=None, group=None):
+        self.optimizer, self.ctx, self.device, self.reducer, self.group = optimizer, ctx, device, reducer, group
         self.decoupled_default = isinstance(optimizer, torch.optim.AdamW)
         where = {}
-        for b in reducer.buckets:
-            if b.group is group:
-                for p, off, n in zip(b.params, b.offsets, b.numels):
-                    where[id(p)] = (off, n)
-        self.m_flat = torch.zeros(group.total_elems, dtype=torch.float32, device=reducer.device)
-        self.v_flat = torch.zeros(group.total_elems, dtype=torch.float32, device=reducer.device)
+        if reducer is not None:
+            for b in reducer.buckets:
+                if b.group is group:
+                    for p, off, n in zip(b.params, b.offsets, b.numels):
+                        where[id(p)] = (off, n)
+            total = group.total_elems
+        else:
+            total = 0
+            for pg in optimizer.param_groups:
+                for p in pg["params"]:
+                    if p.requires_grad and id(p) not in where:
+                        where[id(p)] = (total, p.numel())
+                        total += (p.numel() + 3) & ~3  # keep every moment span 16-byte aligned
+        self.m_flat = torch.zeros(total, dtype=torch.float32, device=device)
+        self.v_flat = torch.zeros(total, dtype=torch.float32, device=device)
         self.tables = []
-        ctx = reducer.rt.ctx
+        self.views = {}  # id(param) -> (exp_avg view, exp_avg_sq view) installed in optimizer.state
+        self.signature = self._signature(optimizer)
         for pg in optimizer.param_groups:
             params = [p for p in pg["params"] if p.requires_grad]
-            ptrs, numels, offs = [], [], []
+            ptrs, numels, offs, gptrs = [], [], [], []
             for p in params:
                 off, n = where[id(p)]
-                st = optimizer.state[p]
-                m_view = self.m_flat[off : off + n].view(p.shape)
-                v_view = self.v_flat[off : off + n].view(p.shape)
-                if "exp_avg" in st:  # resumed run: adopt the existing moments
-                    m_view.copy_(st["exp_avg"])
-                    v_view.copy_(st["exp_avg_sq"])
-                st["exp_avg"], st["exp_avg_sq"] = m_view, v_view
-                if "step" not in st:
-                    st["step"] = torch.tensor(0.0, dtype=torch.float32)
+                self.views[id(p)] = (self.m_flat[off : off + n].view(p.shape), self.v_flat[off : off + n].view(p.shape))
                 ptrs.append(p.data_ptr())
                 numels.append(n)
                 offs.append(off)
-            self.tables.append((params, ctx.make_adam_table(ptrs, numels, offs)))
+                if reducer is not None:
+                    gptrs.append(group.flat.data_ptr() + 4 * off)
+            self.tables.append((params, ctx.make_adam_table(ptrs, numels, offs, gptrs if reducer is not None else None)))
+        self._adopt_state()
+
+    @staticmethod
+    def _signature(optimizer):
+        return tuple((len(pg["params"]), id(pg["params"][0]) if pg["params"] else 0) for pg in optimizer.param_groups)
+
+    def _adopt_state(self):
+        """Make ``optimizer.state[p]['exp_avg'/'exp_avg_sq']`` the views of the flat moment buffers.  Values that
+        are already there (a resumed run, or ``load_state_dict`` replacing the tensors) are copied in first."""
+        for params, _ in self.tables:
+            for p in params:
+                st = self.optimizer.state[p]
+                m_view, v_view = self.views[id(p)]
+                if st.get("exp_avg") is not m_view:
+                    if "exp_avg" in st:
+                        m_view.copy_(st["exp_avg"])
+                        v_view.copy_(st["exp_avg_sq"])
+                    st["exp_avg"], st["exp_avg_sq"] = m_view, v_view
+                if "step" not in st:
+                    st["step"] = torch.tensor(0.0, dtype=torch.float32)
 
     @staticmethod
     def try_build(optimizer):
-        if os.environ.get("B200DP_FUSED_ADAM", "0") != "1" or type(optimizer) not in (torch.optim.Adam, torch.optim.AdamW):
+        if os.environ.get("B200DP_FUSED_ADAM", "1") == "0" or type(optimizer) not in (torch.optim.Adam, torch.optim.AdamW):
             return None
         from .reducer import live_reducers
 
         wanted = [p for pg in optimizer.param_groups for p in pg["params"] if p.requires_grad]
         if not wanted or any(p.dtype != torch.float32 or not p.is_cuda or not p.is_contiguous() for p in wanted):
+            return None
+        if len({p.device for p in wanted}) != 1 or len({id(p) for p in wanted}) != len(wanted):
             return None
         for pg in optimizer.param_groups:
             if pg.get("amsgrad") or pg.get("maximize") or pg.get("capturable") or pg.get("differentiable") or pg.get("fused"):
@@ -86,22 +117,49 @@ class FusedAdamPlan:
             if isinstance(pg["lr"], torch.Tensor) or any(isinstance(b, torch.Tensor) for b in pg["betas"]):
                 return None
         ids = {id(p) for p in wanted}
+        touched = False
         for red in live_reducers():
             if red.is_cuda and ids <= red._managed_ids and torch.float32 in red.groups:
-                return FusedAdamPlan(optimizer, red, red.groups[torch.float32])
-        return None
+                return FusedAdamPlan(optimizer, red.rt.ctx, red.device, red, red.groups[torch.float32])
+            touched = touched or bool(ids & red._managed_ids)
+        if touched:
+            return None  # parameters split over reducers / partly managed: leave it to torch
+        from .runtime import SymmRuntime
+
+        rt = SymmRuntime._instance
+        if rt is None or rt.device != wanted[0].device:
+            return None
+        return FusedAdamPlan(optimizer, rt.ctx, rt.device)
+
+    def _loose_grads(self, params):
+        """Gradient pointers for a loose-layout step, or None when this step is not eligible."""
+        out = []
+        for p in params:
+            g = p.grad
+            if g is None or g.dtype != torch.float32 or g.device != p.device or g.is_sparse or not g.is_contiguous():
+                return None
+            out.append(g.data_ptr())
+        return out
 
     def step(self) -> bool:
         """Run the fused update; False = not applicable right now (caller falls back to optimizer.step())."""
         red = self.reducer
-        if not red.grads_in_buffer():
-            return False
-        ctx = red.rt.ctx
-        stream = torch.cuda.current_stream(red.device).cuda_stream
-        pending = red.take_pending_multiplier()
+        pending = None
+        if red is not None:
+            if not red.grads_in_buffer():
+                return False
+            grads_per_group = [None] * len(self.tables)
+        else:
+            grads_per_group = [self._loose_grads(params) for params, _ in self.tables]
+            if any(g is None for g in grads_per_group):
+                return False
+        self._adopt_state()  # cheap identity checks; heals optimizer.load_state_dict()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        if red is not None:
+            pending = red.take_pending_multiplier()
         mult_ptr = pending.data_ptr() + 4 if pending is not None else None
         found_ptr = None  # without a GradScaler torch applies the update even to non-finite gradients: keep that
-        for pg, (params, table) in zip(self.optimizer.param_groups, self.tables):
+        for pg, (params, table), grads in zip(self.optimizer.param_groups, self.tables, grads_per_group):
             if not params:
                 continue
             steps = [self.optimizer.state[p]["step"] for p in params]
@@ -113,8 +171,8 @@ class FusedAdamPlan:
             l2 = wd if (not decoupled and wd != 0) else 0.0
             bc1 = 1 - beta1**t
             bc2_sqrt = (1 - beta2**t) ** 0.5
-            ctx.multi_adam(table, self.group.flat.data_ptr(), self.m_flat.data_ptr(), self.v_flat.data_ptr(), decay_mul, l2,
-                           beta1, beta2, -(lr / bc1), bc2_sqrt, eps, mult_ptr, found_ptr, stream)  # fmt: skip
+            self.ctx.multi_adam(table, self.m_flat.data_ptr(), self.v_flat.data_ptr(), decay_mul, l2, beta1, beta2,
+                                -(lr / bc1), bc2_sqrt, eps, mult_ptr, found_ptr, stream, grads=grads)  # fmt: skip
         if pending is not None:
             self._keepalive = pending  # the kernels read it asynchronously
         return True
@@ -222,7 +280,10 @@ class AcceleratedOptimizer(torch.optim.Optimizer):
             self._fused_plan_tried = True
             if self.accelerator_state.device.type == "cuda":
                 self._fused_plan = FusedAdamPlan.try_build(self.optimizer)
-        return self._fused_plan is not None and self._fused_plan.step()
+        plan = self._fused_plan
+        if plan is not None and plan.signature != FusedAdamPlan._signature(self.optimizer):
+            self._fused_plan = plan = FusedAdamPlan.try_build(self.optimizer)  # add_param_group() happened
+        return plan is not None and plan.step()
 
     @property
     def step_was_skipped(self) -> bool:

@@ -44,7 +44,8 @@ def parse():
     ap.add_argument("--model", default=os.environ.get("BENCH_MODEL", "gpt2-medium"))
     ap.add_argument("--no-ddp-leg", action="store_true", help="skip the stock torch DDP+NCCL comparison leg")
     ap.add_argument("--no-cpu-leg", action="store_true")
-    ap.add_argument("--fused-adam", action="store_true", help="opt-in: SURVEY 8f row 1, fused AdamW + deferred clip (A/B only)")
+    ap.add_argument("--defer-clip", action="store_true", help="A/B only: let the fused AdamW kernel apply the clip multiplier")
+    ap.add_argument("--torch-adam", action="store_true", help="A/B only: B200DP_FUSED_ADAM=0 (torch's foreach AdamW)")
     return ap.parse_args()
 
 
@@ -221,9 +222,10 @@ def main():
     from accelerate_b200.state import PartialState
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback for the product path)"
-    if args.fused_adam:
-        os.environ["B200DP_FUSED_ADAM"] = "1"
+    if args.defer_clip:
         os.environ["B200DP_DEFER_CLIP"] = "1"
+    if args.torch_adam:
+        os.environ["B200DP_FUSED_ADAM"] = "0"
     acc = Accelerator(mixed_precision="bf16", kwargs_handlers=[DistributedDataParallelKwargs(bucket_cap_mb=25)])
     rank, world, dev = acc.process_index, acc.num_processes, acc.device
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE is {world}: launch with torchrun --nproc-per-node {args.gpus}"
@@ -289,6 +291,13 @@ def main():
     e2e_ms, _, _ = timed(step_e2e, steps)
     rt.ctx.check_status()
     clip_mode = acc.last_clip_mode
+    plan = getattr(opt, "_fused_plan", None)
+    if plan is None:
+        optimizer_step = "torch foreach AdamW"
+    else:
+        optimizer_step = "b200dp_multi_adam, one launch per group, " + ("fusion-buffer gradients" if plan.reducer is not None else "loose gradients")
+        if args.defer_clip and plan.reducer is not None:
+            optimizer_step += " + deferred clip"
 
     # ---- roofline of the dominant kernel of OUR path, CUDA events on the launching stream ----
     peaks, peak_src = measured_peaks()
@@ -319,7 +328,7 @@ def main():
                             "+ clip_grad_norm_(1.0) + AdamW + zero_grad",
                 "global_batch": gb, "per_gpu_batch": B, "seq_len": SEQ, "parallelism": f"dp{world}", "bucket_cap_mb": 25,
                 "l2": "per-step working set (1.4 GB grads + weights + activations) exceeds the 126 MB L2; no flush needed",
-                "clip_mode": clip_mode, "final_loss": float(last_loss.detach()), "fused_adam": bool(args.fused_adam),
+                "clip_mode": clip_mode, "final_loss": float(last_loss.detach()), "optimizer_step": optimizer_step,
             },
             "e2e": {"value": gb * steps / (e2e_ms / 1e3), "unit": "samples/s", "h2d_bytes_per_step": B * SEQ * 8,
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / steps},

@@ -196,21 +196,21 @@ int b200dp_multi_scale(b200dp_ctx* ctx, void* const* ptrs, const size_t* numels,
 /* ---- K9: fused optimizer consumption -------------------------------------
  * Replaces: the ~10 foreach launches of torch.optim.Adam/AdamW.step that AcceleratedOptimizer.step reaches
  * (src/accelerate/optimizer.py:145-181) plus the clip multiply pass, for fp32 parameters whose gradients and
- * moments live in flat buffers laid out like the fusion buffer: one pass reads p, g, m, v and writes p, m, v.
- * params[i] has numels[i] elements; its gradient / moments start at element offs[i] of grads / exp_avg /
- * exp_avg_sq.  Hyper-parameters as torch computes them on the host for step t:
+ * moments live in two flat buffers: one pass reads p, g, m, v and writes p, m, v.  params[i] / grads[i] have
+ * numels[i] elements (grads[i] is a view of the fusion buffer, or any fp32 device tensor); its moments start at
+ * element offs[i] of exp_avg / exp_avg_sq.  Hyper-parameters as torch computes them on the host for step t:
  *   decay_mul = 1 - lr*wd (AdamW; pass 1 for none), l2 = wd (Adam's coupled L2; 0 for none),
  *   neg_step_size = -lr/(1-beta1^t), bc2_sqrt = sqrt(1-beta2^t).
  * mult_ptr (device, may be NULL): gradient multiplier (clip coefficient x 1/loss-scale); found_inf_ptr (device,
  * may be NULL): non-zero skips the whole step. */
-int b200dp_multi_adam(b200dp_ctx* ctx, void* const* params, const size_t* numels, const size_t* offs, int n,
-                      const void* grads, void* exp_avg, void* exp_avg_sq, float decay_mul, float l2, float beta1,
+int b200dp_multi_adam(b200dp_ctx* ctx, void* const* params, const void* const* grads, const size_t* numels,
+                      const size_t* offs, int n, void* exp_avg, void* exp_avg_sq, float decay_mul, float l2, float beta1,
                       float beta2, float neg_step_size, float bc2_sqrt, float eps, const float* mult_ptr,
                       const float* found_inf_ptr, void* stream);
 
 /* ---- K4: bucket pack / unpack (multi-tensor copy) -------------------------------------------
- * Replaces: the per-parameter grad->bucket and bucket->grad copy kernels of the Reducer
- * (torch reducer.hpp:276,286,328).  n (src,dst,bytes) triples, one launch.  use_bulk=1 moves
+ * Replaces: the per-parameter grad->bucket and bucket->grad copy kernels of the Reducer that
+ * src/accelerate/accelerator.py:1892-1894 installs (torch reducer.hpp:276,286,328).  n (src,dst,bytes) triples, one launch.  use_bulk=1 moves
  * 16-byte-aligned spans with cp.async.bulk (TMA engine) through shared memory. */
 int b200dp_pack(b200dp_ctx* ctx, const void* const* srcs, void* const* dsts, const size_t* nbytes,
                 int n, int use_bulk, void* stream);

@@ -178,14 +178,13 @@ def test_fp16_scaler_fused_unscale_clip_and_overflow_skip():
 @pytest.mark.parametrize("cls", [torch.optim.AdamW, torch.optim.Adam])
 @pytest.mark.parametrize("defer", ["0", "1"])
 def test_fused_adam_consumption_matches_torch(cls, defer, monkeypatch):
-    """SURVEY.md §8f row 1 (opt-in B200DP_FUSED_ADAM=1): one multi-tensor kernel instead of torch's foreach Adam/AdamW,
+    """SURVEY.md §8f row 1 (B200DP_FUSED_ADAM, on by default): one multi-tensor kernel instead of torch's foreach Adam/AdamW,
     optionally consuming the deferred clip multiplier; parameters and optimizer state must track torch's own
     optimizer (fp32 rounding) over several steps with a scheduler and two parameter groups."""
     from accelerate_b200 import Accelerator, B200DataParallel
     from accelerate_b200.state import PartialState
 
-    monkeypatch.setenv("B200DP_FUSED_ADAM", "1")
-    monkeypatch.setenv("B200DP_DEFER_CLIP", defer)
+    monkeypatch.setenv("B200DP_DEFER_CLIP", defer)  # fused Adam itself is on by default
     acc = Accelerator()
     model, ref = mlp(3), mlp(3)
     ddp = B200DataParallel(model, device_ids=[0], bucket_cap_mb=0.02)
@@ -224,9 +223,23 @@ def test_fused_adam_consumption_matches_torch(cls, defer, monkeypatch):
         assert float(a["step"]) == float(b["step"]) == 5.0
         assert torch.allclose(a["exp_avg"], b["exp_avg"], rtol=1e-5, atol=1e-8)
         assert torch.allclose(a["exp_avg_sq"], b["exp_avg_sq"], rtol=1e-5, atol=1e-10)
-    # the optimizer is still the user's: state_dict round-trips, and an ineligible step falls back to torch's own
+    # the optimizer is still the user's: state_dict round-trips (load_state_dict replaces the state tensors; the plan
+    # re-adopts them), and an ineligible step falls back to torch's own
     sd = opt.state_dict()
     assert len(sd["state"]) == 4 and sd["param_groups"][0]["lr"] == ref_opt.param_groups[0]["lr"]
+    import copy
+
+    opt.load_state_dict(copy.deepcopy(sd))
+    ref_opt.load_state_dict(copy.deepcopy(ref_opt.state_dict()))
+    ddp(x).square().mean().backward()
+    ref(x).square().mean().backward()
+    opt.step()
+    ref_opt.step()
+    opt.zero_grad(set_to_none=False)
+    ref_opt.zero_grad()
+    for p, q in zip(model.parameters(), ref.parameters()):
+        assert torch.allclose(p, q, rtol=1e-5, atol=1e-7), "after load_state_dict"
+        assert float(opt.optimizer.state[p]["step"]) == 6.0
     opt.zero_grad(set_to_none=True)
     ddp(x).square().mean().backward()
     for p in model.parameters():
@@ -234,4 +247,55 @@ def test_fused_adam_consumption_matches_torch(cls, defer, monkeypatch):
     before = rt.ctx.launches
     opt.step()
     assert rt.ctx.launches == before, "fallback must not launch the fused kernel"
+    rt.ctx.check_status()
+
+
+@pytest.mark.parametrize("cls", [torch.optim.AdamW, torch.optim.Adam])
+def test_fused_adam_loose_gradients_single_process(cls):
+    """The same fused step without a reducer (one process: the reference does not wrap the model either): gradient
+    pointers are collected per step from ``param.grad``; a step with a missing gradient falls back to torch."""
+    from accelerate_b200 import Accelerator
+    from accelerate_b200.state import PartialState
+
+    acc = Accelerator()
+    model, ref = mlp(5), mlp(5)
+    opt = cls(model.parameters(), lr=2e-3, weight_decay=0.05)
+    ref_opt = cls(ref.parameters(), lr=2e-3, weight_decay=0.05, foreach=True)
+    model, opt = acc.prepare(model, opt)
+    assert not hasattr(model, "reducer"), "world size 1 leaves the model unwrapped"
+    rt = PartialState().runtime
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for step in range(4):
+        x = torch.randn(8, 64, device="cuda", generator=g)
+        acc.backward(model(x).square().mean())
+        ref(x).square().mean().backward()
+        tn = acc.clip_grad_norm_(model.parameters(), 0.05)
+        ref_tn = torch.nn.utils.clip_grad_norm_(ref.parameters(), 0.05)
+        assert torch.allclose(tn, ref_tn, rtol=1e-5)
+        before = rt.ctx.launches
+        opt.step()
+        assert opt._fused_plan is not None and opt._fused_plan.reducer is None
+        assert rt.ctx.launches - before == 1, "one fused launch for the single parameter group"
+        ref_opt.step()
+        opt.zero_grad()  # set_to_none=True: next step's gradients are fresh tensors
+        ref_opt.zero_grad()
+        for p, q in zip(model.parameters(), ref.parameters()):
+            assert torch.allclose(p, q, rtol=1e-5, atol=1e-7), step
+    for p, q in zip(model.parameters(), ref.parameters()):
+        a, b = opt.optimizer.state[p], ref_opt.state[q]
+        assert float(a["step"]) == float(b["step"]) == 4.0
+        assert torch.allclose(a["exp_avg"], b["exp_avg"], rtol=1e-5, atol=1e-8)
+        assert torch.allclose(a["exp_avg_sq"], b["exp_avg_sq"], rtol=1e-5, atol=1e-10)
+    # a parameter without a gradient: torch skips it, so must we -> the plan declines and torch's step runs
+    acc.backward(model(x).square().mean())
+    ref(x).square().mean().backward()
+    first, ref_first = next(iter(model.parameters())), next(iter(ref.parameters()))
+    first.grad = None
+    ref_first.grad = None
+    before = rt.ctx.launches
+    opt.step()
+    ref_opt.step()
+    assert rt.ctx.launches == before
+    for p, q in zip(model.parameters(), ref.parameters()):
+        assert torch.allclose(p, q, rtol=1e-5, atol=1e-7)
     rt.ctx.check_status()
