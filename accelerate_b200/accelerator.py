@@ -543,15 +543,15 @@ class Accelerator:
         out = torch.empty(3, dtype=torch.float32, device=self.device)
         if not by_dtype:
             return out[0].zero_()
-        if not hasattr(self, "_mt_slot_base"):
-            self._mt_slot_base = rt.reserve_slots(64)
-        slot = self._mt_slot_base
+        if not hasattr(rt, "_mt_slot_base"):
+            rt._mt_slot_base = rt.reserve_slots(64)  # one reservation per process: the launches are stream-ordered
+        slot = rt._mt_slot_base
         for dtype, grads in by_dtype.items():
             used = rt.ctx.multi_stats([g.data_ptr() for g in grads], [g.numel() for g in grads], native_dtype(dtype), slot, st)
             slot += used
-            if slot - self._mt_slot_base > 64:
+            if slot - rt._mt_slot_base > 64:
                 raise RuntimeError("too many gradient tensors for the multi-tensor clip")
-        rt.ctx.finalize_norm(self._mt_slot_base, slot - self._mt_slot_base, False, norm_type, max_norm, None, out.data_ptr(), st)
+        rt.ctx.finalize_norm(rt._mt_slot_base, slot - rt._mt_slot_base, False, norm_type, max_norm, None, out.data_ptr(), st)
         for dtype, grads in by_dtype.items():
             rt.ctx.multi_scale([g.data_ptr() for g in grads], [g.numel() for g in grads], native_dtype(dtype), out.data_ptr() + 4, st)
         return out[0]

@@ -707,7 +707,7 @@ __global__ void __launch_bounds__(kStreamThreads) multi_scale_kernel(const __gri
 
 // ------------------------------------------------------------------------------------------------
 // K9: fused optimizer consumption: one pass Adam/AdamW over fp32 parameters whose
-// gradients and moments live in flat buffers with the fusion-buffer layout.  Arithmetic follows torch's
+// moments live in flat buffers (gradients: fusion-buffer views or loose tensors).  Arithmetic follows torch's
 // foreach implementation (torch/optim/adam.py `_multi_tensor_adam`, non-capturable branch) operation by
 // operation in float32: decoupled decay `p *= 1 - lr*wd` (AdamW) or `g += wd*p` (Adam), `m.lerp_(g, 1-b1)`,
 // `v = v*b2 + (1-b2)*g*g`, `denom = sqrt(v)/sqrt(1-b2^t) + eps`, `p += (-lr/(1-b1^t)) * (m/denom)`.
@@ -732,16 +732,22 @@ struct AdamHyper {
   float eps;
 };
 
+// Roundings follow torch's CUDA foreach functors as nvcc compiles them (a + alpha*b contracts into one fma):
+//   _foreach_add(g, p, alpha=wd)            -> fma(wd, p, g)
+//   _foreach_lerp_(m, g, w)                 -> fma(w, g - m, m)             (|w| < 0.5, else g - (g-m)*(1-w))
+//   _foreach_mul_(v, b2); _foreach_addcmul_ -> v = v*b2; v = fma(1-b2, g*g, v)
+//   _foreach_sqrt / _foreach_div_ / _foreach_add_ -> sqrt.rn, div.rn, add
+//   _foreach_addcdiv_(p, m, denom, step)    -> fma(step, m / denom, p)
 __device__ __forceinline__ void adam_update(float& p, float g, float& m, float& v, const AdamHyper& h, float mult) {
   g = __fmul_rn(g, mult);
   if (h.decay_mul != 1.0f) p = __fmul_rn(p, h.decay_mul);
-  if (h.l2 != 0.0f) g = __fadd_rn(g, __fmul_rn(h.l2, p));
-  const float diff = __fsub_rn(g, m);  // torch lerp: |w| < 0.5 ? start + w*diff : end - diff*(1-w)
-  m = (fabsf(h.lerp_w) < 0.5f) ? __fadd_rn(m, __fmul_rn(h.lerp_w, diff)) : __fsub_rn(g, __fmul_rn(diff, 1.0f - h.lerp_w));
+  if (h.l2 != 0.0f) g = __fmaf_rn(h.l2, p, g);
+  const float diff = __fsub_rn(g, m);
+  m = (fabsf(h.lerp_w) < 0.5f) ? __fmaf_rn(h.lerp_w, diff, m) : __fsub_rn(g, __fmul_rn(diff, 1.0f - h.lerp_w));
   v = __fmul_rn(v, h.beta2);
-  v = __fadd_rn(v, __fmul_rn(__fmul_rn(h.one_minus_beta2, g), g));
+  v = __fmaf_rn(h.one_minus_beta2, __fmul_rn(g, g), v);
   const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), h.bc2_sqrt), h.eps);
-  p = __fadd_rn(p, __fmul_rn(h.neg_step_size, __fdiv_rn(m, denom)));
+  p = __fmaf_rn(h.neg_step_size, __fdiv_rn(m, denom), p);
 }
 
 __global__ void __launch_bounds__(kStreamThreads) multi_adam_kernel(const __grid_constant__ AdamTable t,

@@ -182,25 +182,32 @@ def bucket_assignment(sizes_bytes, first_cap=1 << 20, cap=25 << 20):
 # a8 / §8f row 1: the optimizer step the reduced gradients feed   (reference: optimizer.py:145-181 ->
 # torch/optim/adam.py `_multi_tensor_adam`, non-capturable branch; AdamW = decoupled weight decay)
 # --------------------------------------------------------------------------------------------
+def _fma(a, b, c):
+    """float32 fused multiply-add: the product of two float32 is exact in float64; the sum is rounded to float64 and
+    then to float32 (double rounding can differ from a true fma in the last bit, rarely: the tests use a tolerance)."""
+    return (np.asarray(a, dtype=np.float64) * np.asarray(b, dtype=np.float64) + np.asarray(c, dtype=np.float64)).astype(F32)
+
+
 def adam_step(p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, decoupled=True, mult=1.0):
-    """One Adam/AdamW update in float32, operation by operation as torch's foreach implementation does it.
-    ``step`` is the 1-based step count AFTER the increment.  Returns new (p, m, v)."""
+    """One Adam/AdamW update in float32, operation by operation as torch's foreach implementation does it on CUDA
+    (``a + alpha*b`` inside one functor is a single fma there).  ``step`` is the 1-based step count AFTER the
+    increment.  Returns new (p, m, v)."""
     p, g, m, v = (np.asarray(a, dtype=F32).copy() for a in (p, g, m, v))
     g = g * F32(mult)
     if weight_decay != 0:
         if decoupled:
             p = p * F32(1 - lr * weight_decay)
         else:
-            g = g + F32(weight_decay) * p
+            g = _fma(F32(weight_decay), p, g)
     w = F32(1 - beta1)
     diff = g - m
-    m = m + w * diff if abs(float(w)) < 0.5 else g - diff * (F32(1.0) - w)
+    m = _fma(w, diff, m) if abs(float(w)) < 0.5 else g - diff * (F32(1.0) - w)
     v = v * F32(beta2)
-    v = v + (F32(1 - beta2) * g) * g
+    v = _fma(F32(1 - beta2), g * g, v)
     bc1 = 1 - beta1**step
     bc2_sqrt = (1 - beta2**step) ** 0.5
     denom = np.sqrt(v) / F32(bc2_sqrt) + F32(eps)
-    p = p + F32(-(lr / bc1)) * (m / denom)
+    p = _fma(F32(-(lr / bc1)), m / denom, p)
     return p, m, v
 
 
