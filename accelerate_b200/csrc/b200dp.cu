@@ -971,22 +971,22 @@ extern "C" int b200dp_multi_scale(b200dp_ctx* c, void* const* ptrs, const size_t
 // K9
 // ------------------------------------------------------------------------------------------------
 extern "C" int b200dp_multi_adam(b200dp_ctx* c, void* const* params, const void* const* grads, const size_t* numels,
-                                 const size_t* offs, int n, void* exp_avg, void* exp_avg_sq, float decay_mul, float l2,
-                                 float beta1, float beta2, float neg_step_size, float bc2_sqrt, float eps,
+                                 const size_t* offs, int n, void* exp_avg, void* exp_avg_sq, double decay_mul, double l2,
+                                 double beta1, double beta2, double neg_step_size, double bc2_sqrt, double eps,
                                  const float* mult_ptr, const float* found_inf_ptr, void* stream) {
   if (!c || (n > 0 && (!params || !grads || !numels || !offs)) || !exp_avg || !exp_avg_sq)
     return fail(B200DP_EINVAL, "null argument");
   DeviceGuard g(c->device);
   cudaStream_t st = (cudaStream_t)stream;
   AdamHyper h;
-  h.decay_mul = decay_mul;
-  h.l2 = l2;
-  h.lerp_w = 1.0f - beta1;
-  h.beta2 = beta2;
-  h.one_minus_beta2 = 1.0f - beta2;
-  h.neg_step_size = neg_step_size;
-  h.bc2_sqrt = bc2_sqrt;
-  h.eps = eps;
+  h.decay_mul = float(decay_mul);
+  h.l2 = float(l2);
+  h.lerp_w = float(1.0 - beta1);  // differences in double, one rounding: what torch's Python side hands its kernels
+  h.beta2 = float(beta2);
+  h.one_minus_beta2 = float(1.0 - beta2);
+  h.neg_step_size = float(neg_step_size);
+  h.bc2_sqrt = float(bc2_sqrt);
+  h.eps = float(eps);
   static thread_local AdamTable t;
   for (int lo = 0; lo < n; lo += kMTMax) {
     const int cnt = (n - lo) < kMTMax ? (n - lo) : kMTMax;

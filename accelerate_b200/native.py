@@ -155,8 +155,8 @@ def load():
             "b200dp_cast": [vp, vp, i, vp, i, sz, c_float, i, vp],
             "b200dp_multi_stats": [vp, POINTER(vp), POINTER(sz), i, i, i, vp],
             "b200dp_multi_scale": [vp, POINTER(vp), POINTER(sz), i, i, vp, vp],
-            "b200dp_multi_adam": [vp, POINTER(vp), POINTER(vp), POINTER(sz), POINTER(sz), i, vp, vp, c_float, c_float, c_float,
-                                  c_float, c_float, c_float, c_float, vp, vp, vp],
+            "b200dp_multi_adam": [vp, POINTER(vp), POINTER(vp), POINTER(sz), POINTER(sz), i, vp, vp, c_double, c_double,
+                                  c_double, c_double, c_double, c_double, c_double, vp, vp, vp],
             "b200dp_pack": [vp, POINTER(vp), POINTER(vp), POINTER(sz), i, i, vp],
             "b200dp_pull": [vp, i, sz, sz, vp, sz, i, i, i, i, vp],
             "b200dp_push": [vp, i, i, vp, sz, i, c_double, vp, i, vp],

@@ -201,12 +201,14 @@ int b200dp_multi_scale(b200dp_ctx* ctx, void* const* ptrs, const size_t* numels,
  * element offs[i] of exp_avg / exp_avg_sq.  Hyper-parameters as torch computes them on the host for step t:
  *   decay_mul = 1 - lr*wd (AdamW; pass 1 for none), l2 = wd (Adam's coupled L2; 0 for none),
  *   neg_step_size = -lr/(1-beta1^t), bc2_sqrt = sqrt(1-beta2^t).
+ * They are doubles because torch derives 1-beta1 and 1-beta2 in double before rounding to float
+ * (float(1 - 0.999) and 1.0f - 0.999f differ by 5e-5 relative).
  * mult_ptr (device, may be NULL): gradient multiplier (clip coefficient x 1/loss-scale); found_inf_ptr (device,
  * may be NULL): non-zero skips the whole step. */
 int b200dp_multi_adam(b200dp_ctx* ctx, void* const* params, const void* const* grads, const size_t* numels,
-                      const size_t* offs, int n, void* exp_avg, void* exp_avg_sq, float decay_mul, float l2, float beta1,
-                      float beta2, float neg_step_size, float bc2_sqrt, float eps, const float* mult_ptr,
-                      const float* found_inf_ptr, void* stream);
+                      const size_t* offs, int n, void* exp_avg, void* exp_avg_sq, double decay_mul, double l2,
+                      double beta1, double beta2, double neg_step_size, double bc2_sqrt, double eps,
+                      const float* mult_ptr, const float* found_inf_ptr, void* stream);
 
 /* ---- K4: bucket pack / unpack (multi-tensor copy) -------------------------------------------
  * Replaces: the per-parameter grad->bucket and bucket->grad copy kernels of the Reducer that

@@ -328,3 +328,62 @@ def test_full_size_properties(rt):
         rt.ctx.check_status()
     finally:
         rt.free_segment(seg)
+
+
+@pytest.mark.parametrize("decoupled", [True, False])
+def test_multi_adam_matches_oracle(rt, decoupled):
+    """K9 through the C ABI vs oracle.adam_step (itself pinned on torch.optim.Adam/AdamW): ragged and misaligned
+    tensors, more tensors than one table holds, the device-side multiplier and the found-inf skip.  float32 with
+    identical operation order; the oracle emulates fma through float64 (rare last-bit differences), hence 2e-6."""
+    from accelerate_b200 import native
+
+    sizes = [1, 3, 4, 257, 4096 + 5, 70000] + [9] * (native.MT_MAX + 20)
+    g = torch.Generator(device="cpu").manual_seed(11)
+    host = {k: [] for k in "pgmv"}
+    for n in sizes:
+        host["p"].append(torch.randn(n, generator=g) * 0.5)
+        host["g"].append(torch.randn(n, generator=g) * 1e-2)
+        host["m"].append(torch.randn(n, generator=g) * 1e-2)
+        host["v"].append(torch.rand(n, generator=g) * 1e-4 + 1e-8)
+    offs, total = [], 0
+    for n in sizes:
+        offs.append(total)
+        total += n  # moments deliberately NOT padded: odd offsets take the scalar path
+    m_flat = torch.cat(host["m"]).to(rt.device)
+    v_flat = torch.cat(host["v"]).to(rt.device)
+    # parameters / gradients: separate allocations, the second one misaligned by one element
+    p_dev = [t.to(rt.device) for t in host["p"]]
+    g_dev = [t.to(rt.device) for t in host["g"]]
+    odd = torch.empty(sizes[1] + 1, device=rt.device)
+    odd[1:].copy_(host["g"][1])
+    g_dev[1] = odd[1:]
+    lr, beta1, beta2, eps, wd, step = 3e-4, 0.9, 0.999, 1e-8, 0.1, 3
+    mult = torch.tensor([0.0, 0.625, 0.0], device=rt.device)  # finalize_norm's layout: [norm, multiplier, found_inf]
+    table = rt.ctx.make_adam_table([t.data_ptr() for t in p_dev], sizes, offs, [t.data_ptr() for t in g_dev])
+    decay_mul = (1 - lr * wd) if decoupled else 1.0
+    l2 = 0.0 if decoupled else wd
+    bc1, bc2_sqrt = 1 - beta1**step, (1 - beta2**step) ** 0.5
+
+    def launch(found_ptr):
+        rt.ctx.multi_adam(table, m_flat.data_ptr(), v_flat.data_ptr(), decay_mul, l2, beta1, beta2, -(lr / bc1), bc2_sqrt,
+                          eps, mult.data_ptr() + 4, found_ptr, stream())  # fmt: skip
+
+    # found_inf set: nothing may change
+    mult[2] = 1.0
+    launch(mult.data_ptr() + 8)
+    torch.cuda.synchronize()
+    assert torch.equal(m_flat.cpu(), torch.cat(host["m"])) and torch.equal(v_flat.cpu(), torch.cat(host["v"]))
+    assert all(torch.equal(d.cpu(), h) for d, h in zip(p_dev, host["p"]))
+    mult[2] = 0.0
+    launch(mult.data_ptr() + 8)
+    torch.cuda.synchronize()
+    m_got, v_got = m_flat.cpu().numpy(), v_flat.cpu().numpy()
+    for i, n in enumerate(sizes):
+        want_p, want_m, want_v = oracle.adam_step(
+            host["p"][i].numpy(), host["g"][i].numpy(), host["m"][i].numpy(), host["v"][i].numpy(), step, lr, beta1, beta2,
+            eps, wd, decoupled=decoupled, mult=0.625,
+        )  # fmt: skip
+        np.testing.assert_allclose(p_dev[i].cpu().numpy(), want_p, rtol=2e-6, atol=1e-9, err_msg=f"param {i}")
+        np.testing.assert_allclose(m_got[offs[i] : offs[i] + n], want_m, rtol=2e-6, atol=1e-10, err_msg=f"exp_avg {i}")
+        np.testing.assert_allclose(v_got[offs[i] : offs[i] + n], want_v, rtol=2e-6, atol=1e-14, err_msg=f"exp_avg_sq {i}")
+    rt.ctx.check_status()
