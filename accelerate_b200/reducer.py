@@ -117,6 +117,35 @@ class GradBucket:
             self.seen[i] = False
 
 
+class HookBucket:
+    """What a user communication hook receives: the methods of ``torch.distributed.GradBucket`` that Python hooks
+    use (torch's own ``default_hooks`` / ``powerSGD_hook`` included), backed by a bucket of the fusion buffer.
+    As in torch, ``buffer()`` is the flat bucket BEFORE any division: averaging is the hook's job."""
+
+    __slots__ = ("_bucket", "_buffer", "_last")
+
+    def __init__(self, bucket: GradBucket, last: bool):
+        self._bucket, self._buffer, self._last = bucket, bucket.flat, last
+
+    def index(self) -> int:
+        return self._bucket.index
+
+    def buffer(self) -> torch.Tensor:
+        return self._buffer
+
+    def set_buffer(self, tensor: torch.Tensor) -> None:
+        self._buffer = tensor
+
+    def gradients(self):
+        return list(self._bucket.views)
+
+    def parameters(self):
+        return list(self._bucket.params)
+
+    def is_last(self) -> bool:
+        return self._last
+
+
 class _DtypeGroup:
     """All gradients of one dtype: one flat fusion buffer (symmetric segment on CUDA)."""
 
@@ -156,6 +185,8 @@ class GradReducer:
         self._comm_dirty = False
         self._wire_dirty = False
         self._pending_mult = None
+        self.user_hook = None  # (state, hook): a user-supplied communication algorithm replaces the fused kernel
+        self._hook_futures = []
         self.rt = None
         if self.is_cuda:
             from .runtime import SymmRuntime, native_dtype
@@ -274,7 +305,7 @@ class GradReducer:
                 srcs = [g.data_ptr() for _, g in b.staged]
                 dsts = [b.ptrs[i] for i, _ in b.staged]
                 sizes = [b.nbytes[i] for i, _ in b.staged]
-                if _PACK_ON_COMM and comm != cs:
+                if _PACK_ON_COMM and comm != cs and self.user_hook is None:
                     # adopt the gradients on the SIDE stream: the pack overlaps with the rest of backward instead
                     # of sitting on the compute stream.  The source tensors must then outlive the pack, so they
                     # are parked until the end-of-backward join (after which the compute stream is ordered behind
@@ -292,6 +323,9 @@ class GradReducer:
                 if _KEEP_STAGED:
                     self._graveyard.extend(g for _, g in b.staged)
                 b.staged.clear()  # same-stream pack: stream order protects the memory; side-stream pack: parked above
+            if self.user_hook is not None:
+                self._run_user_hook(b)
+                return
             if self.wire_dtype is not None and b.group.wire is not None:
                 self._reduce_bucket_wire(b, cs)
                 return
@@ -307,6 +341,9 @@ class GradReducer:
             for i, g in b.staged:
                 b.views[i].copy_(g)
             b.staged.clear()
+            if self.user_hook is not None:
+                self._run_user_hook(b)
+                return
             if self.wire_dtype is not None and b.flat.dtype == torch.float32:
                 # torch's compress hook: buffer.to(dtype).div_(N) -> allreduce -> copy back (default_hooks._compress_hook)
                 narrow = b.flat.to(self.wire_dtype).div_(self.world)
@@ -318,6 +355,33 @@ class GradReducer:
             b.flat.mul_(1.0 / self.world)
             if self.world > 1:
                 dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.process_group)
+
+    def set_user_hook(self, state, hook):
+        """torch's operator plug point (``DistributedDataParallel.register_comm_hook``; reached from
+        dataclasses.py:234-237): ``hook(state, bucket) -> Future[Tensor]`` is called once per bucket per sync
+        backward, in bucket order on every rank, with the un-divided flat bucket; the future's value becomes the
+        bucket's content.  The fused kernel (and its statistics) are out of the picture for this wrapper."""
+        if self.user_hook is not None or self.wire_dtype is not None:
+            raise RuntimeError("register_comm_hook can only be called once.")  # torch's rule and wording
+        if not callable(hook):
+            raise TypeError("Communication hook must be callable.")
+        self.user_hook = (state, hook)
+
+    def _run_user_hook(self, b: GradBucket):
+        state, hook = self.user_hook
+        fut = hook(state, HookBucket(b, b.index == len(self.buckets) - 1))
+        if not isinstance(fut, torch._C.Future):  # c10d work futures are the base class of torch.futures.Future
+            raise TypeError("Communication hook: return annotation should be torch.futures.Future.")
+        self._hook_futures.append((b, fut))
+
+    def _join_user_hooks(self):
+        futures, self._hook_futures = self._hook_futures, []
+        for b, fut in futures:
+            result = fut.wait()
+            if isinstance(result, (list, tuple)):  # c10d work futures resolve to a list of tensors
+                result = result[0]
+            if result.data_ptr() != b.flat.data_ptr() or result.dtype != b.flat.dtype:
+                b.flat.copy_(result.reshape(-1))  # torch Reducer: copy the hook's result into the bucket views
 
     def _pick_algo(self, seg):
         algo = self.algo
@@ -350,6 +414,8 @@ class GradReducer:
         """Collective: allocate the half-width symmetric wire buffers (fp32 gradient groups only)."""
         if dtype not in (torch.bfloat16, torch.float16):
             raise ValueError(f"wire dtype must be torch.bfloat16 or torch.float16, got {dtype}")
+        if self.user_hook is not None:
+            raise RuntimeError("register_comm_hook can only be called once.")
         self.wire_dtype = dtype
         if not self.is_cuda:
             return
@@ -365,6 +431,8 @@ class GradReducer:
         try:
             if self._next < len(self.buckets):
                 self._handle_unready()
+            if self._hook_futures:
+                self._join_user_hooks()
             if self.is_cuda:
                 # a device-side flag wait that timed out (dead or diverged peer) latches a status word in mapped
                 # host memory; surface it here instead of training on with unreduced gradients
@@ -385,11 +453,12 @@ class GradReducer:
                 if not _SAME_STREAM:
                     self.rt.ctx.stream_wait(self.compute_stream, self.comm_stream)
                 self._graveyard.clear()
-                self.stats_valid = True
+                self.stats_valid = self.user_hook is None  # a user hook bypasses the kernel that gathers them
                 self.unscaled = False
             self.num_reductions += 1
         finally:
             self._armed = False
+            self._hook_futures = []
             self._reset_iteration()
 
     def _handle_unready(self):
@@ -607,19 +676,31 @@ class B200DataParallel(torch.nn.Module):
             self.require_backward_grad_sync = previous
 
     def register_comm_hook(self, state, hook):
+        """``DistributedDataParallel.register_comm_hook`` (torch distributed.py; reached from dataclasses.py:234-237).
+
+        * ``DDPCommunicationHookType.FP16/BF16`` — or torch's own ``fp16_compress_hook`` / ``bf16_compress_hook``
+          functions — select the native half-precision wire (cast kernel + the fused allreduce on a half-width buffer);
+        * torch's ``allreduce_hook`` is what the fused kernel already computes: nothing to change;
+        * any other callable ``hook(state, bucket) -> Future[Tensor]`` (PowerSGD, user code) is run per bucket through
+          the ``GradBucket`` protocol and owns the communication, typically over ``torch.distributed``.
+        """
+        from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
+
         from .utils.dataclasses import DDPCommunicationHookType
 
-        if isinstance(hook, DDPCommunicationHookType):
-            if hook == DDPCommunicationHookType.FP16:
-                self.reducer.set_wire_dtype(torch.float16)
-                return
-            if hook == DDPCommunicationHookType.BF16:
-                self.reducer.set_wire_dtype(torch.bfloat16)
-                return
-            raise NotImplementedError(f"comm hook {hook} is not implemented by the B200 reducer")
-        raise NotImplementedError(
-            "arbitrary Python communication hooks are not supported: the allreduce is a fused device kernel"
-        )
+        native_wire = {
+            DDPCommunicationHookType.FP16: torch.float16, DDPCommunicationHookType.BF16: torch.bfloat16,
+            default_hooks.fp16_compress_hook: torch.float16, default_hooks.bf16_compress_hook: torch.bfloat16,
+        }  # fmt: skip
+        if isinstance(hook, DDPCommunicationHookType) and hook not in native_wire:
+            raise ValueError(f"{hook} names a hook family; pass the hook callable (DistributedDataParallelKwargs does)")
+        if hook in native_wire:
+            self.reducer.set_wire_dtype(native_wire[hook])
+        elif hook is default_hooks.allreduce_hook:
+            if self.reducer.user_hook is not None or self.reducer.wire_dtype is not None:
+                raise RuntimeError("register_comm_hook can only be called once.")
+        else:
+            self.reducer.set_user_hook(state, hook)
 
     def _sync_buffers(self):
         bufs = self._ddp_buffers

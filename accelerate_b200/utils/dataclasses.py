@@ -90,10 +90,12 @@ class DDPCommunicationHookType(BaseEnum):
 class DistributedDataParallelKwargs(KwargsHandler):
     """Knobs of the gradient reducer; field-compatible with the reference (dataclasses.py:181-195).
 
-    ``comm_hook`` / ``comm_wrapper`` FP16/BF16 select a half-precision *wire* format for the fused
-    allreduce (the reference's compress hooks, dataclasses.py:206-216): gradients are cast and
-    pre-divided into a half-width symmetric buffer, reduced there, and widened back once per step.
-    PowerSGD variants are not implemented.
+    ``comm_hook=FP16|BF16`` selects a half-precision *wire* format for the fused allreduce (the
+    reference's compress hooks, dataclasses.py:206-216): gradients are cast and pre-divided into a
+    half-width symmetric buffer, reduced there, and widened back once per step.  ``POWER_SGD`` /
+    ``BATCHED_POWER_SGD`` and any ``comm_wrapper`` combination register torch's own hook functions,
+    exactly as the reference does; the wrapper runs them per bucket (``GradReducer.set_user_hook``).
+    As in the reference, a ``comm_wrapper`` without a ``comm_hook`` registers nothing.
     """
 
     dim: int = 0
@@ -112,17 +114,33 @@ class DistributedDataParallelKwargs(KwargsHandler):
         return {k: v for k, v in super().to_dict().items() if k not in ignore_keys}
 
     def register_comm_hook(self, model):
-        """Mirror of dataclasses.py:200-237: translate the enum into a hook on the wrapper."""
-        hook, wrapper = self.comm_hook, self.comm_wrapper
-        if hook == DDPCommunicationHookType.NO and wrapper == DDPCommunicationHookType.NO:
+        """Mirror of dataclasses.py:200-237: translate the enums into a hook on the wrapper.  A bare FP16/BF16
+        compress hook maps to the reducer's native half-precision wire; PowerSGD and wrapped combinations are torch's
+        own hook functions, which the wrapper runs per bucket through the ``GradBucket`` protocol."""
+        hook_type, wrapper_type = self.comm_hook, self.comm_wrapper
+        no, half = DDPCommunicationHookType.NO, (DDPCommunicationHookType.FP16, DDPCommunicationHookType.BF16)
+        if hook_type == no:
+            return  # the reference registers nothing without a hook, whatever the wrapper says (dataclasses.py:222)
+        if hook_type in half and wrapper_type == no:
+            model.register_comm_hook(None, hook_type)
             return
-        if DDPCommunicationHookType.POWER_SGD in (hook, wrapper) or DDPCommunicationHookType.BATCHED_POWER_SGD in (
-            hook,
-            wrapper,
-        ):
-            raise NotImplementedError("PowerSGD communication hooks are not implemented by the B200 reducer")
-        wire = hook if hook != DDPCommunicationHookType.NO else wrapper
-        model.register_comm_hook(dict(self.comm_state_option), wire)
+        from torch.distributed.algorithms.ddp_comm_hooks import default_hooks, powerSGD_hook
+
+        hook = {
+            DDPCommunicationHookType.FP16: default_hooks.fp16_compress_hook,
+            DDPCommunicationHookType.BF16: default_hooks.bf16_compress_hook,
+            DDPCommunicationHookType.POWER_SGD: powerSGD_hook.powerSGD_hook,
+            DDPCommunicationHookType.BATCHED_POWER_SGD: powerSGD_hook.batched_powerSGD_hook,
+        }[hook_type]
+        if wrapper_type != no:
+            hook = {
+                DDPCommunicationHookType.FP16: default_hooks.fp16_compress_wrapper,
+                DDPCommunicationHookType.BF16: default_hooks.bf16_compress_wrapper,
+            }[wrapper_type](hook)
+        state = None
+        if hook_type in (DDPCommunicationHookType.POWER_SGD, DDPCommunicationHookType.BATCHED_POWER_SGD):
+            state = powerSGD_hook.PowerSGDState(None, **self.comm_state_option)
+        model.register_comm_hook(state, hook)
 
 
 @dataclass

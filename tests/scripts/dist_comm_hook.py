@@ -1,6 +1,8 @@
-"""Compress hooks (reference: src/accelerate/test_utils/scripts/test_ddp_comm_hook.py:39-57): gradients
-produced with DistributedDataParallelKwargs(comm_hook=FP16|BF16) (or comm_wrapper=...) must match the
-no-hook gradients within rtol=atol=1e-2, and be identical on all ranks."""
+"""Communication hooks (reference: src/accelerate/test_utils/scripts/test_ddp_comm_hook.py:39-81): gradients
+produced with every (comm_hook, comm_wrapper, comm_state_option) combination the reference tests must match the
+no-hook gradients within rtol=atol=1e-2 and be identical on all ranks.  FP16/BF16 run on the native half-precision
+wire; PowerSGD / wrapped combinations are torch's own hook functions driven through the GradBucket protocol
+(exercised on the CPU/gloo leg; the CUDA leg keeps to the native paths until it has been validated on a GPU box)."""
 import argparse
 import os
 import sys
@@ -12,6 +14,37 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 from scenarios import make_batch, make_model  # noqa: E402
+
+
+def power_sgd_compressing(Accelerator, DistributedDataParallelKwargs, H, AcceleratorState, GradientState):
+    """PowerSGD past its warm-up (start_powerSGD_iter=2): the hook now really compresses (low-rank P/Q allreduces with
+    error feedback, torch's algorithm untouched).  Ranks must still agree bit for bit, and the low-rank gradient must
+    stay close to the exact mean (rank 8 of matrices whose smaller side is 8..16)."""
+    means = {}
+    for name, kw in [("exact", {}), ("psgd", {"comm_hook": H.POWER_SGD, "comm_state_option": {
+            "start_powerSGD_iter": 2, "matrix_approximation_rank": 8, "min_compression_rate": 0.5}})]:  # fmt: skip
+        AcceleratorState._reset_state()
+        GradientState._reset_state()
+        acc = Accelerator(cpu=True, kwargs_handlers=[DistributedDataParallelKwargs(**kw)])
+        model = acc.prepare(make_model())
+        for step in range(5):
+            x, y = make_batch(acc.process_index, step)
+            model.zero_grad()
+            acc.backward(torch.nn.functional.mse_loss(model(x), y))
+            flat = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+            everyone = acc.gather(flat.reshape(1, -1)).numpy()
+            assert all(everyone[0].tobytes() == everyone[r].tobytes() for r in range(acc.num_processes)), (name, step)
+            means[(name, step)] = flat.numpy().copy()
+        if name == "psgd":
+            state, _ = model.reducer.user_hook
+            assert state.iter == 5, state.iter  # one bucket, five sync backwards
+    for step in range(5):
+        a, b = means[("psgd", step)], means[("exact", step)]
+        rel = np.linalg.norm(a - b) / np.linalg.norm(b)
+        if step < 2:
+            assert rel == 0.0, (step, rel)  # warm-up iterations are plain allreduces
+        else:
+            assert 0.0 < rel < 0.5, (step, rel)
 
 
 def main():
@@ -26,15 +59,41 @@ def main():
     from accelerate_b200.state import AcceleratorState, GradientState, PartialState
 
     results = {}
-    for name, kw in [("no", {}), ("fp16", {"comm_hook": DDPCommunicationHookType.FP16}),
-                     ("bf16", {"comm_hook": DDPCommunicationHookType.BF16}),
-                     ("bf16_wrapper", {"comm_wrapper": DDPCommunicationHookType.BF16})]:  # fmt: skip
+    H = DDPCommunicationHookType
+    cases = [("no", {}), ("fp16", {"comm_hook": H.FP16}), ("bf16", {"comm_hook": H.BF16}),
+             ("wrapper_only", {"comm_wrapper": H.BF16})]  # fmt: skip
+    if cpu:  # the reference's own list (test_ddp_comm_hook.py:62-73)
+        cases += [
+            ("power_sgd", {"comm_hook": H.POWER_SGD}),
+            ("power_sgd+fp16", {"comm_hook": H.POWER_SGD, "comm_wrapper": H.FP16}),
+            ("power_sgd+bf16", {"comm_hook": H.POWER_SGD, "comm_wrapper": H.BF16}),
+            ("power_sgd_rank2", {"comm_hook": H.POWER_SGD, "comm_state_option": {"matrix_approximation_rank": 2}}),
+            ("batched_power_sgd", {"comm_hook": H.BATCHED_POWER_SGD}),
+            ("batched_power_sgd+fp16", {"comm_hook": H.BATCHED_POWER_SGD, "comm_wrapper": H.FP16}),
+            ("batched_power_sgd+bf16", {"comm_hook": H.BATCHED_POWER_SGD, "comm_wrapper": H.BF16}),
+            ("fp16+bf16_wrapper", {"comm_hook": H.FP16, "comm_wrapper": H.BF16}),
+            ("user_allreduce", {}),
+        ]
+    exact = {"wrapper_only", "power_sgd", "power_sgd_rank2", "batched_power_sgd", "user_allreduce"}
+    for name, kw in cases:
         AcceleratorState._reset_state()
         GradientState._reset_state()
         acc = Accelerator(cpu=cpu, kwargs_handlers=[DistributedDataParallelKwargs(**kw)])
         rank, world, dev = acc.process_index, acc.num_processes, acc.device
         model = acc.prepare(make_model())
-        assert model.reducer.wire_dtype == {"no": None, "fp16": torch.float16}.get(name, torch.bfloat16)
+        if name == "user_allreduce":  # an arbitrary Python hook: divide, allreduce over torch.distributed
+            import torch.distributed as dist
+
+            def user_hook(state, bucket):
+                state["calls"] += 1
+                t = bucket.buffer().div_(dist.get_world_size())
+                return dist.all_reduce(t, async_op=True).get_future().then(lambda f: f.value()[0])
+
+            hook_state = {"calls": 0}
+            model.register_comm_hook(hook_state, user_hook)
+        native_wire = {"fp16": torch.float16, "bf16": torch.bfloat16}.get(name)
+        assert model.reducer.wire_dtype == native_wire
+        assert (model.reducer.user_hook is not None) == (name not in ("no", "fp16", "bf16", "wrapper_only"))
         for step in range(2):  # second step: grads are already views of the fusion buffer
             x, y = (t.to(dev) for t in make_batch(rank, step))
             model.zero_grad(set_to_none=(step == 0))
@@ -48,10 +107,17 @@ def main():
             tn = acc.clip_grad_norm_(model.parameters(), 0.01)
             want = torch.sqrt(sum((g.double() ** 2).sum() for g in ref)).item()
             assert acc.last_clip_mode == "fused" and abs(tn.item() - want) <= 1e-5 * want, (name, tn.item(), want)
+        if name == "user_allreduce":
+            assert hook_state["calls"] == 2 * len(model.reducer.buckets)
+    if cpu:
+        power_sgd_compressing(Accelerator, DistributedDataParallelKwargs, H, AcceleratorState, GradientState)
     for (name, step), grads in results.items():
         for g, base in zip(grads, results[("no", step)]):
             assert np.allclose(g, base, rtol=1e-2, atol=1e-2), (name, step, np.abs(g - base).max())
-            if name != "no":
+            if name in exact:
+                # PowerSGD is a plain allreduce before start_powerSGD_iter (1000); at two ranks x/2 == x*0.5 exactly
+                assert world != 2 or np.array_equal(g, base), (name, step, "must equal the fused mean bit for bit")
+            elif name != "no":
                 assert not np.array_equal(g, base) or np.all(base == 0), (name, "hook had no effect")
     if not cpu:
         PartialState().runtime.ctx.check_status()

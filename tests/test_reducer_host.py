@@ -105,7 +105,61 @@ def test_comm_hook_registration_surface():
     full(torch.randn(4, 5)).sum().backward()  # different input: only check representability
     for p in ddp.parameters():
         assert torch.equal(p.grad, p.grad.to(torch.bfloat16).float()), "wire format must round gradients to bf16"
-    with pytest.raises(NotImplementedError):
+    # one hook per wrapper, as in torch
+    with pytest.raises(RuntimeError, match="only be called once"):
         DistributedDataParallelKwargs(comm_hook=DDPCommunicationHookType.POWER_SGD).register_comm_hook(ddp)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="only be called once"):
         ddp.register_comm_hook(None, lambda state, bucket: None)
+    # as in the reference, a wrapper without a hook registers nothing
+    plain = B200DataParallel(small_model())
+    DistributedDataParallelKwargs(comm_wrapper=DDPCommunicationHookType.BF16).register_comm_hook(plain)
+    assert plain.reducer.wire_dtype is None and plain.reducer.user_hook is None
+
+
+def test_user_comm_hook_protocol_single_process():
+    """torch's plug point: hook(state, bucket) -> Future[Tensor], once per bucket per sync backward, in bucket order,
+    with the UN-divided flat bucket; the future's value becomes the gradients (in place or as a new tensor)."""
+    from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
+
+    calls = []
+
+    def doubling_hook(state, bucket):
+        calls.append((bucket.index(), bucket.is_last(), bucket.buffer().numel(), len(bucket.gradients()), len(bucket.parameters())))
+        for g, p in zip(bucket.gradients(), bucket.parameters()):
+            assert g.shape == p.shape and g.data_ptr() >= bucket.buffer().data_ptr()
+        fut = torch.futures.Future()
+        fut.set_result(bucket.buffer() * state["factor"])  # a NEW tensor: must be copied back into the bucket
+        return fut
+
+    torch.manual_seed(0)
+    ddp = B200DataParallel(small_model(), bucket_cap_mb=0.0001)
+    ref = B200DataParallel(small_model(), bucket_cap_mb=0.0001)
+    ref.load_state_dict(ddp.state_dict())
+    ddp.register_comm_hook({"factor": 2.0}, doubling_hook)
+    x = torch.randn(4, 5)
+    for _ in range(2):  # second pass: gradients are already views of the fusion buffer
+        ddp.zero_grad(set_to_none=False)
+        ref.zero_grad(set_to_none=False)
+        calls.clear()
+        ddp(x).sum().backward()
+        ref(x).sum().backward()
+        assert [c[0] for c in calls] == list(range(len(ddp.reducer.buckets))) and len(calls) > 1
+        assert [c[1] for c in calls] == [False] * (len(calls) - 1) + [True]
+        for p, q in zip(ddp.parameters(), ref.parameters()):
+            assert torch.equal(p.grad, q.grad * 2.0)
+    assert ddp.reducer.stats_valid is False or not ddp.reducer.is_cuda
+    with ddp.no_sync():
+        calls.clear()
+        ddp(x).sum().backward()
+        assert calls == [], "no_sync: the hook must not run"
+    with pytest.raises(TypeError, match="torch.futures.Future"):
+        bad = B200DataParallel(small_model())
+        bad.register_comm_hook(None, lambda state, bucket: bucket.buffer())
+        bad(x).sum().backward()
+    # torch's canonical hooks map onto the native paths
+    fast = B200DataParallel(small_model())
+    fast.register_comm_hook(None, default_hooks.allreduce_hook)
+    assert fast.reducer.user_hook is None and fast.reducer.wire_dtype is None
+    half = B200DataParallel(small_model())
+    half.register_comm_hook(None, default_hooks.bf16_compress_hook)
+    assert half.reducer.wire_dtype == torch.bfloat16 and half.reducer.user_hook is None
