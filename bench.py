@@ -304,6 +304,12 @@ def main():
     roofline, extra = kernel_roofline(acc, model, rt, world, peaks, peak_src)
 
     # ---- stock torch DDP + NCCL + torch clip_grad_norm_ on the same box (what the reference delegates to) ----
+    # ---- the fused optimizer step (K9), timed alone; rank-local, never allowed to take the result down ----
+    try:
+        adam_probe = adam_kernel_probe(opt, rt, peaks, peak_src)
+    except Exception as err:
+        adam_probe = {"kernel": "multi_adam_kernel", "error": repr(err)}
+
     ddp_leg = None
     if not args.no_ddp_leg and (world == 1 or PartialState().backend == "nccl"):
         del opt
@@ -337,6 +343,8 @@ def main():
             "roofline": roofline,
         }  # fmt: skip
         line.update(extra)
+        if adam_probe is not None:
+            line["roofline_adam_kernel"] = adam_probe
         if ddp_leg is not None:
             line["torch_ddp_nccl"] = ddp_leg
         if cpu is not None:
@@ -344,6 +352,48 @@ def main():
         emit(line)
     acc.wait_for_everyone()
     PartialState().destroy_process_group()
+
+
+def adam_kernel_probe(opt, rt, peaks, peak_src):
+    """CUDA-event time of one fused Adam/AdamW step (all parameter groups) on the optimizer's own tables and moment
+    buffers, after the measured steps.  Launched with lr = 0 (neg_step_size 0, no decay), so parameters keep their
+    values; algorithmic bytes = 28 per element (read p, g, m, v; write p, m, v)."""
+    import torch
+
+    plan = getattr(opt, "_fused_plan", None)
+    if plan is None:
+        return None
+    st = torch.cuda.current_stream().cuda_stream
+    groups = [(params, table) for params, table in plan.tables if params]
+    elems = sum(p.numel() for params, _ in groups for p in params)
+    if plan.reducer is None:  # loose layout: gradients are separate tensors, freed by zero_grad -> scratch ones
+        scratch = [[torch.zeros_like(p) for p in params] for params, _ in groups]
+        gptrs = [[g_.data_ptr() for g_ in gs] for gs in scratch]
+    else:
+        gptrs = [None] * len(groups)
+
+    def launch():
+        for (_, table), g_ in zip(groups, gptrs):
+            rt.ctx.multi_adam(table, plan.m_flat.data_ptr(), plan.v_flat.data_ptr(), 1.0, 0.0, 0.9, 0.999, 0.0, 1.0, 1e-8,
+                              None, None, st, grads=g_)  # fmt: skip
+
+    reps = 10
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * reps)]
+    for _ in range(3):
+        launch()
+    for i in range(reps):
+        ev[2 * i].record()
+        launch()
+        ev[2 * i + 1].record()
+    torch.cuda.synchronize()
+    ms = sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(reps)) / reps
+    nbytes = 28 * elems
+    peak = float(peaks["hbm_gbs"])
+    achieved = nbytes / (ms * 1e-3) / 1e9
+    return {"kernel": "multi_adam_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})", "traffic": None,
+            "bytes_per_step": nbytes, "ms_per_step": ms, "launches_per_step": len(groups),
+            "gradients": "fusion buffer" if plan.reducer is not None else "loose tensors"}  # fmt: skip
 
 
 def kernel_roofline(acc, model, rt, world, peaks, peak_src):
