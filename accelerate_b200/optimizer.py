@@ -27,6 +27,18 @@ def _to_device(obj, device):
     return obj
 
 
+def _has_step_hooks(optimizer) -> bool:
+    """User-registered optimizer step hooks must fire around ``optimizer.step``: such optimizers keep torch's step."""
+    import torch.optim.optimizer as O
+
+    return bool(
+        getattr(optimizer, "_optimizer_step_pre_hooks", None)
+        or getattr(optimizer, "_optimizer_step_post_hooks", None)
+        or getattr(O, "_global_optimizer_pre_hooks", None)
+        or getattr(O, "_global_optimizer_post_hooks", None)
+    )
+
+
 class FusedAdamPlan:
     """Fused optimizer consumption; ``B200DP_FUSED_ADAM=0`` turns it off.
 
@@ -283,7 +295,11 @@ class AcceleratedOptimizer(torch.optim.Optimizer):
         plan = self._fused_plan
         if plan is not None and plan.signature != FusedAdamPlan._signature(self.optimizer):
             self._fused_plan = plan = FusedAdamPlan.try_build(self.optimizer)  # add_param_group() happened
-        return plan is not None and plan.step()
+        if plan is None or _has_step_hooks(self.optimizer) or not plan.step():
+            return False
+        # torch's LRScheduler patches optimizer.step to learn that a step happened before scheduler.step()
+        self.optimizer._opt_called = True
+        return True
 
     @property
     def step_was_skipped(self) -> bool:
