@@ -185,6 +185,7 @@ class GradReducer:
         self._comm_dirty = False
         self._wire_dirty = False
         self._pending_mult = None
+        self._locally_undefined = []  # (bucket, i) whose gradient was None when an unused parameter was filled in
         self.user_hook = None  # (state, hook): a user-supplied communication algorithm replaces the fused kernel
         self._hook_futures = []
         self.rt = None
@@ -258,6 +259,7 @@ class GradReducer:
             for b in self.buckets:
                 b.slot = self.slot_base + b.index
         self._managed_ids = frozenset(id(p) for p in params)
+        self._param_index = {id(p): k for k, p in enumerate(params)}
         self._hooks = []
         for b in self.buckets:
             for i, p in enumerate(b.params):
@@ -455,10 +457,13 @@ class GradReducer:
                 self._graveyard.clear()
                 self.stats_valid = self.user_hook is None  # a user hook bypasses the kernel that gathers them
                 self.unscaled = False
+            if self.find_unused_parameters:
+                self._restore_globally_unused()
             self.num_reductions += 1
         finally:
             self._armed = False
             self._hook_futures = []
+            self._locally_undefined = []
             self._reset_iteration()
 
     def _handle_unready(self):
@@ -471,12 +476,44 @@ class GradReducer:
                 "Wrap with DistributedDataParallelKwargs(find_unused_parameters=True) if parts of the model are "
                 "conditionally unused."
             )
+        # torch Reducer (mark_variable_ready for an unused parameter): a defined gradient — e.g. one accumulated under
+        # no_sync — goes into the bucket as it is; an undefined one contributes zeros, and stays undefined afterwards
+        # if NO rank used the parameter (`_restore_globally_unused`)
         for b, i in missing:
-            b.views[i].zero_()  # contributes 0 to the mean; the slice may hold last step's values
-            b.params[i].grad = b.views[i]
+            p, view = b.params[i], b.views[i]
+            g = p.grad
+            if g is None:
+                view.zero_()
+                self._locally_undefined.append((b, i))
+                p.grad = view
+            elif g.data_ptr() != b.ptrs[i]:
+                b.staged.append((i, g if g.is_contiguous() else g.contiguous()))
+                p.grad = view
             b.seen[i] = True
             b.pending -= 1
         self._launch_ready()
+
+    def _restore_globally_unused(self):
+        """``find_unused_parameters=True``: a parameter that no rank used in this backward keeps ``grad=None`` (torch
+        Reducer::finalize_bucket_dense, "globally unused").  Every rank takes part in one small integer allreduce per
+        sync backward, exactly like DDP's ``local_used_map`` reduction."""
+        undefined, self._locally_undefined = self._locally_undefined, []
+        if self.world > 1:
+            flags = [1] * len(self.params)
+            index = self._param_index
+            for b, i in undefined:
+                flags[index[id(b.params[i])]] = 0
+            used = torch.tensor(flags, dtype=torch.int32, device=self.device)
+            if self.is_cuda:
+                from .collectives import all_reduce
+
+                used = all_reduce(used)
+            else:
+                dist.all_reduce(used, op=dist.ReduceOp.SUM, group=self.process_group)
+            used = used.tolist()
+            undefined = [(b, i) for b, i in undefined if used[index[id(b.params[i])]] == 0]
+        for b, i in undefined:
+            b.params[i].grad = None
 
     def _reset_iteration(self):
         self._next = 0

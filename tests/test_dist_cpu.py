@@ -33,3 +33,10 @@ def test_bert_accumulation_clip_buffers_cpu():
     """BASELINE.json config 4 shape (scaled down): bf16, gradient_accumulation_steps=4, clip on the sync step, buffers."""
     out = run_distributed("dist_bert.py", 2, "--device", "cpu", timeout=600)
     assert out.count("BERT_CHECK_OK") == 2, out[-3000:]
+
+
+def test_unused_parameters_match_torch_ddp():
+    """find_unused_parameters=True: grad=None for globally unused parameters, accumulated gradients reduced as they
+    are — bit-equal to torch DistributedDataParallel on the same process group."""
+    out = run_distributed("dist_unused.py", 2, timeout=300)
+    assert out.count("UNUSED_OK") == 2, out[-3000:]

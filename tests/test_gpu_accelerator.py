@@ -132,8 +132,13 @@ def test_unused_parameters():
     strict.reducer.remove_hooks()
     lenient = B200DataParallel(TwoHeads().cuda(), device_ids=[0], find_unused_parameters=True)
     lenient(x, False).sum().backward()
-    assert lenient.module.b.weight.grad is not None and lenient.module.b.weight.grad.abs().sum() == 0
+    assert lenient.module.b.weight.grad is None, "globally unused: grad stays undefined, as with torch DDP"
     assert lenient.module.a.weight.grad.abs().sum() > 0
+    with lenient.no_sync():
+        lenient(x, True).sum().backward()
+    kept = lenient.module.b.weight.grad.clone()
+    lenient(x, False).sum().backward()  # b unused in the sync backward: its accumulated gradient is reduced as it is
+    assert torch.equal(lenient.module.b.weight.grad, kept) and kept.abs().sum() > 0
 
 
 def test_fp16_scaler_fused_unscale_clip_and_overflow_skip():

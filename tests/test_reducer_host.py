@@ -91,7 +91,14 @@ def test_unused_parameters_policy():
     strict.reducer.remove_hooks()
     lenient = B200DataParallel(Two(), find_unused_parameters=True)
     lenient(torch.randn(3, 2)).sum().backward()
-    assert lenient.module.b.weight.grad is not None and float(lenient.module.b.weight.grad.abs().sum()) == 0.0
+    # torch DDP: a parameter no rank used keeps grad=None (Reducer "globally unused")
+    assert lenient.module.b.weight.grad is None and lenient.module.a.weight.grad is not None
+    # a gradient accumulated under no_sync is reduced as it is by a sync backward that does not touch the parameter
+    with lenient.no_sync():
+        lenient(torch.randn(3, 2), use_b=True).sum().backward()
+    kept = lenient.module.b.weight.grad.clone()
+    lenient(torch.randn(3, 2)).sum().backward()
+    assert torch.equal(lenient.module.b.weight.grad, kept) and float(kept.abs().sum()) > 0
 
 
 def test_comm_hook_registration_surface():
