@@ -3,8 +3,9 @@
 it (multi-rank commands must not be wrapped in ncu).  World size 1: the allreduce kernel's NVLink side is absent,
 its HBM side (read S, write S, statistics) is what the capture shows.
 
-    ncu --set full --clock-control none --import-source on -k regex:"allreduce_inplace|pack_bulk|pack_kernel|scale_flat|push_kernel" \
-        -c 12 -o gpurun_out/prof_r01_kernels python benchmarks/kernel_probe.py
+    ncu --set full --clock-control none --import-source on \
+        -k regex:"allreduce_inplace|pack_bulk|pack_kernel|scale_flat|push_kernel|multi_adam" \
+        -c 14 -o gpurun_out/prof_kernels python benchmarks/kernel_probe.py
 """
 import os
 import sys
@@ -33,6 +34,17 @@ def main():
     for s in sizes:
         dsts.append(flat.data_ptr() + off)
         off += (s + 31) // 32 * 32
+    # fused Adam/AdamW step on a GPT-2-medium-like tensor list (24 blocks' worth of 1024x1024 matrices + vectors):
+    # gradients = the tensors above, moments in two flat buffers, 28 algorithmic bytes per element
+    params = [torch.randn_like(g) for g in grads]
+    numels = [g.numel() for g in grads]
+    moffs, total = [], 0
+    for k in numels:
+        moffs.append(total)
+        total += (k + 3) & ~3
+    m_flat = torch.zeros(total, device=rt.device)
+    v_flat = torch.zeros(total, device=rt.device)
+    adam_table = rt.ctx.make_adam_table([p.data_ptr() for p in params], numels, moffs, [g.data_ptr() for g in grads])
     small = torch.randn(4096, device=rt.device)
     staging = rt.ensure_staging()
     small_out = torch.empty_like(small)
@@ -46,6 +58,8 @@ def main():
         rt.ctx.pack([g.data_ptr() for g in grads], dsts, sizes, 1, st)
         rt.ctx.pack([g.data_ptr() for g in grads], dsts, sizes, 0, st)
         rt.ctx.push(staging.seg, 1, small.data_ptr(), small.numel() * 4, native.F32, 1.0, small_out.data_ptr(), native.CH_PUSH, st)
+        rt.ctx.multi_adam(adam_table, m_flat.data_ptr(), v_flat.data_ptr(), 1 - 1e-4 * 0.01, 0.0, 0.9, 0.999, -1e-4 / (1 - 0.9 ** (rep + 1)),
+                          (1 - 0.999 ** (rep + 1)) ** 0.5, 1e-8, out.data_ptr() + 4, None, st)  # fmt: skip
     torch.cuda.synchronize()
     rt.ctx.check_status()
     print("probe ok")
