@@ -755,13 +755,19 @@ class B200DataParallel(torch.nn.Module):
             dev = torch.device(self.reducer.device.type, self.device_ids[0])
             inputs = send_to_device(inputs, dev)
             kwargs = send_to_device(kwargs, dev)
-        if self._ddp_buffers and self.broadcast_buffers and self.require_forward_param_sync and self.training:
+        # torch DDP, _pre_forward / _post_forward (distributed.py:1553-1650): buffers are re-broadcast before a forward
+        # iff the PREVIOUS forward was a gradient-syncing one (require_forward_param_sync), whatever the train/eval
+        # mode; the sync decision for the coming backward is latched here, from require_backward_grad_sync
+        # 
+        if self._ddp_buffers and self.broadcast_buffers and self.require_forward_param_sync:
             self._sync_buffers()
-        if torch.is_grad_enabled() and self.require_backward_grad_sync:
-            self.reducer.prepare_for_backward([])  # latched at forward time, as in torch
-        else:
-            self.reducer._armed = False
-        return self.module(*inputs, **kwargs)
+        output = self.module(*inputs, **kwargs)
+        will_sync = torch.is_grad_enabled() and self.require_backward_grad_sync
+        self.require_forward_param_sync = will_sync
+        if will_sync:
+            self.reducer.prepare_for_backward([])
+        # a non-syncing forward does not disarm: like torch's expect_autograd_hooks_, only the end of a reduction does
+        return output
 
 
 def find_reducers(model_or_models):

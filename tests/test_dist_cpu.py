@@ -40,3 +40,11 @@ def test_unused_parameters_match_torch_ddp():
     are — bit-equal to torch DistributedDataParallel on the same process group."""
     out = run_distributed("dist_unused.py", 2, timeout=300)
     assert out.count("UNUSED_OK") == 2, out[-3000:]
+
+
+@pytest.mark.parametrize("seed", [7, 3])
+def test_differential_against_torch_ddp(seed):
+    """A random, rank-consistent sequence of sync / no_sync / zero_grad / eval / repeated-forward steps on a model with
+    tied weights and BatchNorm buffers: gradients AND buffers bit-equal to torch DistributedDataParallel (gloo, N=2)."""
+    out = run_distributed("dist_ddp_diff.py", 2, timeout=300, env={"DDP_DIFF_SEED": str(seed)})
+    assert out.count("DDP_DIFF_OK") == 2, out[-3000:]
