@@ -1,0 +1,32 @@
+"""The same user training script under the reference and under this package (2 ranks, CPU/gloo): every value the loop
+can observe must be identical — at two ranks the gradient mean is exact, so even the final weights match bit for bit.
+Runs only where the reference tree exists (the build container); its outputs for the GPU box are tests/golden/."""
+
+import json
+import os
+
+import pytest
+
+from conftest import run_distributed
+
+REF = "/root/reference/src"
+pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+def test_training_loop_matches_the_reference(tmp_path, variant):
+    outs = {}
+    for impl in ("reference", "ours"):
+        base = str(tmp_path / impl)
+        env = {"PYTHONDONTWRITEBYTECODE": "1"}
+        out = run_distributed("dist_loop_diff.py", 2, "--impl", impl, "--out", base, "--variant", str(variant), env=env, timeout=600)
+        assert out.count("LOOP_DONE") == 2, out[-3000:]
+        outs[impl] = [json.load(open(f"{base}.rank{r}.json")) for r in range(2)]
+    for r in range(2):
+        ref, ours = outs["reference"][r], outs["ours"][r]
+        assert len(ref["steps"]) == len(ours["steps"]) > 0
+        for k, (a, b) in enumerate(zip(ref["steps"], ours["steps"])):
+            assert a == b, (variant, r, k, a, b)
+        assert ref["eval"] == ours["eval"], (variant, r)
+        assert ref["reduced_probe"] == ours["reduced_probe"]
+        assert ref["final_state_sha256"] == ours["final_state_sha256"], (variant, r)
