@@ -159,6 +159,8 @@ def pad_to_max(t: torch.Tensor, dim: int, pad_index, pad_first: bool) -> torch.T
     max_size = max(s[dim] for s in sizes)
     if max_size == t.shape[dim]:
         return t
+    if isinstance(pad_index, torch.Tensor) and pad_index.numel() == 1:
+        pad_index = pad_index.item()  # e.g. split_between_processes(apply_padding=True) passes `inputs[-1]`
     # `tensor.new_zeros(..) + pad_index` may promote (int tensor, float pad): follow torch's rule
     res_dtype = torch.result_type(t, pad_index)
     src = t if t.dtype == res_dtype else t.to(res_dtype)
@@ -168,7 +170,8 @@ def pad_to_max(t: torch.Tensor, dim: int, pad_index, pad_first: bool) -> torch.T
     new_shape[dim] = max_size
     out = torch.empty(new_shape, dtype=src.dtype, device=src.device)
     es = src.element_size()
-    if es > 8:  # complex128: no native pattern; rare enough to take the 3-op route
+    if es > 8 or isinstance(pad_index, torch.Tensor):
+        # complex128 has no native pattern and a tensor-valued pad (a whole row) broadcasts: rare enough for the 3-op route
         out = src.new_zeros(new_shape) + pad_index
         idx = [slice(None)] * len(new_shape)
         idx[dim] = slice(max_size - src.shape[dim], max_size) if pad_first else slice(0, src.shape[dim])

@@ -174,15 +174,29 @@ class PartialState(_Borg):
         start = self.process_index * per + min(self.process_index, extra)
         end = start + per + (1 if self.process_index < extra else 0)
 
+        width = per + (1 if extra > 0 else 0)  # the longest share
+
         def take(seq):
-            part = seq[start:end]
-            if apply_padding and extra and len(part) < per + 1:
-                last = seq[-1:]
-                part = torch.cat([part, last]) if isinstance(part, torch.Tensor) else list(part) + list(last)
+            # semantics of state.py:477-492: a rank past the end still gets the last element; lists are padded with
+            # the share's own last element, tensors with the input's last row through pad_across_processes (a collective)
+            if not isinstance(seq, (list, tuple, torch.Tensor)):
+                return seq
+            part = seq[-1:] if start >= len(seq) else seq[start:end]
+            if apply_padding:
+                if isinstance(part, torch.Tensor):
+                    from .utils.operations import pad_across_processes, send_to_device
+
+                    part = pad_across_processes(send_to_device(part, self.device), pad_index=seq[-1])
+                else:
+                    part += [part[-1]] * (width - len(part))
             return part
 
         if isinstance(inputs, dict):
-            yield {k: take(v) for k, v in inputs.items()}
+            if not all(len(v) == length for v in inputs.values()):
+                raise ValueError("All values in the dictionary must have the same length")
+            for key in inputs.keys():  # the reference rewrites the caller's dict in place and yields it
+                inputs[key] = take(inputs[key])
+            yield inputs
         else:
             yield take(inputs)
 

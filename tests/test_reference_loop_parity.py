@@ -30,3 +30,18 @@ def test_training_loop_matches_the_reference(tmp_path, variant):
         assert ref["eval"] == ours["eval"], (variant, r)
         assert ref["reduced_probe"] == ours["reduced_probe"]
         assert ref["final_state_sha256"] == ours["final_state_sha256"], (variant, r)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_collective_and_process_control_api_matches_the_reference(tmp_path, world):
+    outs = {}
+    for impl in ("reference", "ours"):
+        base = str(tmp_path / impl)
+        out = run_distributed("dist_api_diff.py", world, "--impl", impl, "--out", base, env={"PYTHONDONTWRITEBYTECODE": "1"}, timeout=600)
+        assert out.count("API_DONE") == world, out[-3000:]
+        outs[impl] = [json.load(open(f"{base}.rank{r}.json")) for r in range(world)]
+    for r in range(world):
+        ref, ours = outs["reference"][r], outs["ours"][r]
+        assert ref.keys() == ours.keys()
+        for key in ref:
+            assert ref[key] == ours[key], (world, r, key, ref[key], ours[key])
