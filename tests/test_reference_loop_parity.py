@@ -45,3 +45,20 @@ def test_collective_and_process_control_api_matches_the_reference(tmp_path, worl
         assert ref.keys() == ours.keys()
         for key in ref:
             assert ref[key] == ours[key], (world, r, key, ref[key], ours[key])
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_prepared_dataloaders_match_the_reference(tmp_path, world):
+    """~130 (length, batch size, drop_last, split_batches, shard/dispatch/iterable, shuffle, even_batches) cases: every
+    batch on every rank over two epochs, end_of_dataloader/remainder, gather_for_metrics, len, skip_first_batches."""
+    outs = {}
+    for impl in ("reference", "ours"):
+        base = str(tmp_path / impl)
+        out = run_distributed("dist_loader_diff.py", world, "--impl", impl, "--out", base, env={"PYTHONDONTWRITEBYTECODE": "1"}, timeout=900)
+        assert out.count("LOADER_DONE") == world, out[-3000:]
+        outs[impl] = [json.load(open(f"{base}.rank{r}.json")) for r in range(world)]
+    for r in range(world):
+        ref, ours = outs["reference"][r]["runs"], outs["ours"][r]["runs"]
+        assert len(ref) == len(ours) > 50
+        for a, b in zip(ref, ours):
+            assert a == b, (world, r, a["cfg"])
