@@ -18,17 +18,19 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--impl", choices=["ours", "reference"], required=True)
     ap.add_argument("--out", required=True)
-    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--variant", default="all")
     args = ap.parse_args()
     os.environ["ACCELERATE_USE_CPU"] = "yes"
     torch.set_num_threads(1)
     if args.impl == "reference":
         sys.path.insert(0, "/root/reference/src")
         import accelerate as lib
+        from accelerate.state import AcceleratorState, GradientState
         from accelerate.utils import DataLoaderConfiguration, GradientAccumulationPlugin, set_seed
     else:
         sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
         import accelerate_b200 as lib
+        from accelerate_b200.state import AcceleratorState, GradientState
         from accelerate_b200.utils import DataLoaderConfiguration, GradientAccumulationPlugin, set_seed
 
     variants = [
@@ -36,11 +38,37 @@ def main():
         dict(accum=3, n=40, bs=4, split=True, dispatch=False, sync_each_batch=False, seedable=False, drop_last=True),
         dict(accum=2, n=29, bs=3, split=False, dispatch=True, sync_each_batch=True, seedable=False, drop_last=False),
         dict(accum=1, n=26, bs=5, split=False, dispatch=False, sync_each_batch=False, seedable=True, drop_last=False),
+        dict(accum=2, n=33, bs=4, split=False, dispatch=False, sync_each_batch=False, seedable=True, drop_last=False, mp="bf16"),
+        dict(accum=3, n=31, bs=2, split=False, dispatch=False, sync_each_batch=False, seedable=False, drop_last=False,
+             sync_with_dataloader=False, adjust_scheduler=False),
+        dict(accum=2, n=24, bs=4, split=True, dispatch=True, sync_each_batch=False, seedable=False, drop_last=False,
+             step_with_opt=False),
     ]
-    v = variants[args.variant]
+    chosen = range(len(variants)) if args.variant == "all" else [int(args.variant)]
+    logs = {}
+    for vi in chosen:
+        if args.impl == "reference":
+            AcceleratorState._reset_state(True)
+        else:
+            AcceleratorState._reset_state()
+        GradientState._reset_state()
+        logs[str(vi)] = run_variant(lib, variants[vi], DataLoaderConfiguration, GradientAccumulationPlugin, set_seed)
+    import torch.distributed as dist
+
+    rank = dist.get_rank()
+    dist.barrier()
+    with open(f"{args.out}.rank{rank}.json", "w") as f:
+        json.dump(logs, f)
+    print(f"LOOP_DONE {args.impl} rank {rank}", flush=True)
+    dist.destroy_process_group()
+
+
+def run_variant(lib, v, DataLoaderConfiguration, GradientAccumulationPlugin, set_seed):
     accelerator = lib.Accelerator(
-        cpu=True,
-        gradient_accumulation_plugin=GradientAccumulationPlugin(num_steps=v["accum"], sync_each_batch=v["sync_each_batch"]),
+        cpu=True, mixed_precision=v.get("mp"), step_scheduler_with_optimizer=v.get("step_with_opt", True),
+        gradient_accumulation_plugin=GradientAccumulationPlugin(
+            num_steps=v["accum"], sync_each_batch=v["sync_each_batch"], sync_with_dataloader=v.get("sync_with_dataloader", True),
+            adjust_scheduler=v.get("adjust_scheduler", True)),
         dataloader_config=DataLoaderConfiguration(split_batches=v["split"], dispatch_batches=v["dispatch"],
                                                   use_seedable_sampler=v["seedable"]),
     )  # fmt: skip
@@ -97,10 +125,7 @@ def main():
     log["final_state_sha256"] = digest.hexdigest()
     log["reduced_probe"] = [float(a).hex() for a in accelerator.reduce(torch.tensor([1.5 + rank, -2.0 * rank]), "mean").tolist()]
     accelerator.wait_for_everyone()
-    with open(f"{args.out}.rank{rank}.json", "w") as f:
-        json.dump(log, f)
-    print(f"LOOP_DONE {args.impl} rank {rank}", flush=True)
-    accelerator.end_training()
+    return log
 
 
 if __name__ == "__main__":

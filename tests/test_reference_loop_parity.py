@@ -13,23 +13,24 @@ REF = "/root/reference/src"
 pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
-def test_training_loop_matches_the_reference(tmp_path, variant):
+def test_training_loop_matches_the_reference(tmp_path):
     outs = {}
     for impl in ("reference", "ours"):
         base = str(tmp_path / impl)
         env = {"PYTHONDONTWRITEBYTECODE": "1"}
-        out = run_distributed("dist_loop_diff.py", 2, "--impl", impl, "--out", base, "--variant", str(variant), env=env, timeout=600)
+        out = run_distributed("dist_loop_diff.py", 2, "--impl", impl, "--out", base, "--variant", "all", env=env, timeout=900)
         assert out.count("LOOP_DONE") == 2, out[-3000:]
         outs[impl] = [json.load(open(f"{base}.rank{r}.json")) for r in range(2)]
     for r in range(2):
-        ref, ours = outs["reference"][r], outs["ours"][r]
-        assert len(ref["steps"]) == len(ours["steps"]) > 0
-        for k, (a, b) in enumerate(zip(ref["steps"], ours["steps"])):
-            assert a == b, (variant, r, k, a, b)
-        assert ref["eval"] == ours["eval"], (variant, r)
-        assert ref["reduced_probe"] == ours["reduced_probe"]
-        assert ref["final_state_sha256"] == ours["final_state_sha256"], (variant, r)
+        assert outs["reference"][r].keys() == outs["ours"][r].keys() and len(outs["ours"][r]) == 7
+        for variant in outs["reference"][r]:
+            ref, ours = outs["reference"][r][variant], outs["ours"][r][variant]
+            assert len(ref["steps"]) == len(ours["steps"]) > 0
+            for k, (a, b) in enumerate(zip(ref["steps"], ours["steps"])):
+                assert a == b, (variant, r, k, a, b)
+            assert ref["eval"] == ours["eval"], (variant, r)
+            assert ref["reduced_probe"] == ours["reduced_probe"]
+            assert ref["final_state_sha256"] == ours["final_state_sha256"], (variant, r)
 
 
 @pytest.mark.parametrize("world", [2, 3])
