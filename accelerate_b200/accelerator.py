@@ -129,6 +129,7 @@ class Accelerator:
 
         self.step = 0
         self._optimizers, self._models, self._schedulers, self._dataloaders = [], [], [], []
+        self._wrappers = []  # B200DataParallel instances handed to the user (their hooks are removed by free_memory)
         self._custom_objects = []
         self.flag_tensor = None
         self.rng_types = rng_types if rng_types is not None else ["generator"]
@@ -377,8 +378,12 @@ class Accelerator:
                 wrapped_model = B200DataParallel(model, **kwargs)
             if self.ddp_handler is not None:
                 self.ddp_handler.register_comm_hook(wrapped_model)
-            self._models[-1] = wrapped_model
+            # like the reference (accelerator.py:1805,1892-1896), `_models` keeps the UNWRAPPED module: save_state /
+            # load_state therefore read and write parameter names without the wrapper's "module." prefix, which is what
+            # makes checkpoints interchangeable between the two libraries in distributed runs
+            self._wrappers.append(wrapped_model)
             model = wrapped_model
+        model._is_accelerate_prepared = True
         return model
 
     def prepare_data_loader(self, data_loader, device_placement=None, slice_fn_for_dispatch=None):
@@ -625,9 +630,9 @@ class Accelerator:
         return skip_first_batches(dataloader, num_batches=num_batches)
 
     def free_memory(self, *objects):
-        for m in self._models:
-            if isinstance(m, B200DataParallel):
-                m.reducer.remove_hooks()
+        for m in self._wrappers:
+            m.reducer.remove_hooks()
+        self._wrappers = []
         self._schedulers, self._optimizers, self._models, self._dataloaders = [], [], [], []
         self.step = 0
         import gc

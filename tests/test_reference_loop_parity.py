@@ -63,3 +63,10 @@ def test_prepared_dataloaders_match_the_reference(tmp_path, world):
         assert len(ref) == len(ours) > 50
         for a, b in zip(ref, ours):
             assert a == b, (world, r, a["cfg"])
+
+
+def test_mid_epoch_resume_is_interchangeable_with_the_reference(tmp_path):
+    """save_state in the middle of an epoch with either library, resume (load_state + skip_first_batches) with either
+    library, 2 ranks: all four combinations end with the weights of an uninterrupted run; same files on disk."""
+    out = run_distributed("dist_resume_diff.py", 2, "--dir", str(tmp_path), env={"PYTHONDONTWRITEBYTECODE": "1"}, timeout=600)
+    assert out.count("RESUME_OK") == 2, out[-3000:]
