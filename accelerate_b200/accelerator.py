@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import contextlib
 import functools
+from collections import OrderedDict
 import math
 import os
 from contextlib import contextmanager
@@ -130,6 +131,7 @@ class Accelerator:
         self.step = 0
         self._optimizers, self._models, self._schedulers, self._dataloaders = [], [], [], []
         self._wrappers = []  # B200DataParallel instances handed to the user (their hooks are removed by free_memory)
+        self._save_model_state_pre_hook, self._load_model_state_pre_hook = OrderedDict(), OrderedDict()
         self._custom_objects = []
         self.flag_tensor = None
         self.rng_types = rng_types if rng_types is not None else ["generator"]
@@ -205,6 +207,23 @@ class Accelerator:
         return self.project_configuration.project_dir
 
     @property
+    def logging_dir(self):
+        return self.project_configuration.logging_dir
+
+    @property
+    def save_iteration(self):
+        return self.project_configuration.iteration
+
+    @property
+    def use_stateful_dataloader(self):
+        return bool(getattr(self.dataloader_config, "use_stateful_dataloader", False))
+
+    @property
+    def multi_device(self):
+        """True when every process drives its own accelerator device (accelerator.py:657-668)."""
+        return self.use_distributed and self.distributed_type == DistributedType.MULTI_GPU
+
+    @property
     def sync_gradients(self):
         return self.gradient_state.sync_gradients
 
@@ -243,6 +262,11 @@ class Accelerator:
         if function is None:
             return functools.partial(self.on_process, process_index=process_index)
         return PartialState().on_process(function, process_index)
+
+    def on_local_process(self, function=None, local_process_index=None):
+        if function is None:
+            return functools.partial(self.on_local_process, local_process_index=local_process_index)
+        return PartialState().on_local_process(function, local_process_index)
 
     @contextmanager
     def main_process_first(self):
@@ -663,6 +687,24 @@ class Accelerator:
                              "The following inputs are invalid:\n" + "\n".join(bad))  # fmt: skip
         self._custom_objects.extend(objects)
 
+    def register_save_state_pre_hook(self, hook):
+        """``hook(models, weights, output_dir)`` runs inside save_state before anything is written
+        (accelerator.py:3547-3577); entries removed from ``weights`` are not saved.  Returns a removable handle."""
+        from torch.utils import hooks
+
+        handle = hooks.RemovableHandle(self._save_model_state_pre_hook)
+        self._save_model_state_pre_hook[handle.id] = hook
+        return handle
+
+    def register_load_state_pre_hook(self, hook):
+        """``hook(models, input_dir)`` runs inside load_state before anything is read (accelerator.py:3714-3743);
+        models removed from the list are not loaded.  Returns a removable handle."""
+        from torch.utils import hooks
+
+        handle = hooks.RemovableHandle(self._load_model_state_pre_hook)
+        self._load_model_state_pre_hook[handle.id] = hook
+        return handle
+
     def save_state(self, output_dir: str = None, safe_serialization: bool = True, **save_model_func_kwargs):
         """Write models, optimizers, schedulers, scaler, RNG states (every rank) and registered objects in the
         reference's on-disk layout (accelerator.py:3579-3712)."""
@@ -684,6 +726,8 @@ class Accelerator:
             self.wait_for_everyone()
         os.makedirs(output_dir, exist_ok=True)
         weights = [self.get_state_dict(m, unwrap=False) for m in self._models]
+        for hook in self._save_model_state_pre_hook.values():
+            hook(self._models, weights, output_dir)
         save_accelerator_state(
             output_dir, weights, [o for o in self._optimizers], [s for s in self._schedulers], self._dataloaders,
             self.process_index, self.step, scaler=self.scaler, save_on_each_node=cfg.save_on_each_node,
@@ -711,11 +755,14 @@ class Accelerator:
             input_dir = os.path.join(folder, names[-1])
         else:
             raise ValueError("No input_dir provided and automatic checkpoint naming is disabled.")
+        models = list(self._models)
+        for hook in self._load_model_state_pre_hook.values():
+            hook(models, input_dir)
         map_location = load_model_func_kwargs.pop("map_location", None)
         if map_location is None:
             map_location = "on_device" if self.num_processes > 1 and self.device.type == "cuda" else "cpu"
         overrides = load_accelerator_state(
-            input_dir, self._models, self._optimizers, self._schedulers, self._dataloaders, self.process_index,
+            input_dir, models, self._optimizers, self._schedulers, self._dataloaders, self.process_index,
             scaler=self.scaler, map_location=map_location, device=self.device, **load_model_func_kwargs,
         )  # fmt: skip
         if "step" in overrides:

@@ -214,6 +214,11 @@ class PartialState(_Borg):
             return lambda f: self.on_process(f, process_index)
         return self._only_if(function, lambda: self.process_index == process_index)
 
+    def on_local_process(self, function=None, local_process_index: int = None):
+        if function is None:
+            return lambda f: self.on_local_process(f, local_process_index)
+        return self._only_if(function, lambda: self.local_process_index == local_process_index)
+
     def _only_if(self, function, predicate):
         if function is None:
             return lambda f: self._only_if(f, predicate)

@@ -26,6 +26,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--impl", choices=["ours", "reference"], required=True)
     ap.add_argument("--out", required=True)
+    ap.add_argument("--project", required=True, help="scratch directory for the checkpointing part")
     args = ap.parse_args()
     os.environ["ACCELERATE_USE_CPU"] = "yes"
     torch.set_num_threads(1)
@@ -40,7 +41,8 @@ def main():
         from accelerate_b200 import utils
         from accelerate_b200.local_sgd import LocalSGD
 
-    acc = lib.Accelerator(cpu=True)
+    project = utils.ProjectConfiguration(project_dir=args.project, automatic_checkpoint_naming=True, total_limit=2)
+    acc = lib.Accelerator(cpu=True, project_config=project)
     rank, world = acc.process_index, acc.num_processes
     g = torch.Generator().manual_seed(11 + rank)
     log = {}
@@ -117,6 +119,56 @@ def main():
                 opt.zero_grad()
                 local_sgd.step()
             log[f"local_sgd_{step}"] = ser(acc.unwrap_model(model).weight)
+
+    @acc.on_local_process(local_process_index=0)
+    def only_local0():
+        return "ran"
+
+    log["on_local"] = only_local0()
+
+    # checkpoint bookkeeping: automatic naming, rotation with total_limit=2, pre-hooks, registered objects
+    class Counter:
+        def __init__(self):
+            self.n = 0
+
+        def state_dict(self):
+            return {"n": self.n}
+
+        def load_state_dict(self, sd):
+            self.n = sd["n"]
+
+    counter = Counter()
+    acc.register_for_checkpointing(counter)
+    seen = []
+    h_save = acc.register_save_state_pre_hook(lambda models, weights, out: seen.append(("save", len(models), sorted(weights[0]), os.path.basename(out))))
+    h_load = acc.register_load_state_pre_hook(lambda models, d: seen.append(("load", len(models), os.path.basename(d))))
+    for k in range(3):
+        counter.n = 10 + k
+        acc.save_state()
+        log[f"save_iteration_{k}"] = acc.save_iteration
+    acc.wait_for_everyone()
+    log["checkpoint_dirs"] = sorted(os.listdir(os.path.join(args.project, "checkpoints")))
+    log["checkpoint_files"] = sorted(os.listdir(os.path.join(args.project, "checkpoints", "checkpoint_2")))
+    counter.n = -1
+    acc.load_state()
+    log["counter_after_load"] = counter.n
+    h_save.remove()
+    h_load.remove()
+    log["hook_calls"] = ser(seen)
+    log["project"] = [os.path.basename(str(acc.project_dir)), acc.logging_dir is None or os.path.basename(str(acc.logging_dir))]
+
+    class Words(torch.utils.data.Dataset):
+        def __len__(self):
+            return 11
+
+        def __getitem__(self, i):
+            return {"id": i, "word": f"w{i}"}
+
+    wdl = acc.prepare(torch.utils.data.DataLoader(Words(), batch_size=2, collate_fn=lambda b: b))
+    collected = []
+    for b in wdl:
+        collected.extend(acc.gather_for_metrics(b, use_gather_object=True))
+    log["gather_objects_for_metrics"] = ser(collected)
 
     dl = acc.prepare(torch.utils.data.DataLoader(list(range(22)), batch_size=3))
     log["skip_first"] = ser([b for b in acc.skip_first_batches(dl, 2)])

@@ -38,7 +38,10 @@ def test_collective_and_process_control_api_matches_the_reference(tmp_path, worl
     outs = {}
     for impl in ("reference", "ours"):
         base = str(tmp_path / impl)
-        out = run_distributed("dist_api_diff.py", world, "--impl", impl, "--out", base, env={"PYTHONDONTWRITEBYTECODE": "1"}, timeout=600)
+        project = tmp_path / f"scratch_{impl}" / "project"
+        project.mkdir(parents=True)
+        out = run_distributed("dist_api_diff.py", world, "--impl", impl, "--out", base, "--project", str(project),
+                              env={"PYTHONDONTWRITEBYTECODE": "1"}, timeout=600)  # fmt: skip
         assert out.count("API_DONE") == world, out[-3000:]
         outs[impl] = [json.load(open(f"{base}.rank{r}.json")) for r in range(world)]
     for r in range(world):
