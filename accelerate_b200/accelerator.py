@@ -335,14 +335,45 @@ class Accelerator:
 
     @contextmanager
     def join_uneven_inputs(self, joinables, even_batches=None):
-        """The P2P allreduce needs every rank in every step; uneven inputs are only supported through
-        ``even_batches=True`` (the default), for which this is a no-op like in single-process runs."""
-        if self.use_distributed and (even_batches is False or not self.even_batches):
-            raise NotImplementedError(
-                "join_uneven_inputs with even_batches=False is not supported: the flag-synchronised allreduce "
-                "kernels require every rank to take part in every step"
-            )
-        yield
+        """Train on uneven per-rank inputs (accelerator.py:1299-1372): inside the context a rank that runs out of
+        batches shadows the others' collectives through torch's ``Join`` (the prepared model is a ``Joinable``).
+        ``even_batches`` temporarily overrides the setting of the prepared map-style dataloaders.  Like the reference,
+        only the one-device-per-process GPU configuration joins; elsewhere the context has no effect."""
+        import warnings
+
+        if self.multi_device:
+            from torch.distributed.algorithms.join import Join
+
+            from .data_loader import DataLoaderDispatcher
+
+            overridden = []
+            if even_batches is not None:
+                iterable_seen = False
+                for idx, dl in enumerate(self._dataloaders):
+                    if isinstance(dl, DataLoaderDispatcher):
+                        iterable_seen = True
+                        continue
+                    overridden.append((idx, dl.batch_sampler.even_batches))
+                    dl.batch_sampler.even_batches = even_batches
+                if iterable_seen:
+                    warnings.warn(
+                        "Overriding even_batches is only supported for map-style datasets, yet some dataloaders given were iterable"
+                    )
+            else:
+                even_batches = self.even_batches
+            try:
+                with Join(joinables, enable=not even_batches, throw_on_early_termination=False):
+                    yield
+            finally:
+                for idx, value in overridden:
+                    self._dataloaders[idx].batch_sampler.even_batches = value
+        else:
+            if self.distributed_type != DistributedType.NO:
+                warnings.warn(
+                    "Joining uneven inputs is only supported for multi-GPU training, as a result `join_uneven_inputs` will have no effect."
+                )
+            with contextlib.nullcontext(joinables):
+                yield
 
     # ------------------------------------------------------------------ prepare
     def prepare(self, *args, device_placement=None):

@@ -42,6 +42,7 @@ from contextlib import contextmanager
 import torch
 import torch.distributed as dist
 from torch.autograd import Variable
+from torch.distributed.algorithms.join import Join, Joinable, JoinHook
 
 from . import native
 
@@ -186,6 +187,7 @@ class GradReducer:
         self._wire_dirty = False
         self._pending_mult = None
         self._locally_undefined = []  # (bucket, i) whose gradient was None when an unused parameter was filled in
+        self._shadowing = False  # inside shadow_backward (a joined rank standing in for a backward it does not run)
         self.user_hook = None  # (state, hook): a user-supplied communication algorithm replaces the fused kernel
         self._hook_futures = []
         self.rt = None
@@ -499,7 +501,7 @@ class GradReducer:
         sync backward, exactly like DDP's ``local_used_map`` reduction."""
         undefined, self._locally_undefined = self._locally_undefined, []
         if self.world > 1:
-            flags = [1] * len(self.params)
+            flags = [0 if self._shadowing else 1] * len(self.params)  # a joined rank used nothing
             index = self._param_index
             for b, i in undefined:
                 flags[index[id(b.params[i])]] = 0
@@ -514,6 +516,27 @@ class GradReducer:
             undefined = [(b, i) for b, i in undefined if used[index[id(b.params[i])]] == 0]
         for b, i in undefined:
             b.params[i].grad = None
+
+    def shadow_backward(self):
+        """A rank that ran out of data (torch ``Join``) stands in for one sync backward of the others: it contributes
+        zeros to every bucket, in bucket order, and takes part in every collective a real backward would issue
+        (torch ``_match_all_reduce_for_bwd_pass`` / ``_match_unused_params_allreduce``).  Unlike torch, the in-place
+        reduction leaves the OTHER ranks' mean gradient in this rank's fusion buffer."""
+        self.prepare_for_backward([])
+        self._shadowing = True
+        try:
+            with torch.no_grad():
+                for group in self.groups.values():
+                    group.flat.zero_()
+            for b in self.buckets:
+                b.pending = 0
+                b.staged.clear()
+                for i in range(len(b.seen)):
+                    b.seen[i] = True
+            self._launch_ready()
+            self._finalize_backward()
+        finally:
+            self._shadowing = False
 
     def _reset_iteration(self):
         self._next = 0
@@ -627,24 +650,24 @@ class GradReducer:
                 torch._foreach_div_([p.data for p, _, _ in mine], float(self.world))  # the reference's `/= N`
                 group.flat.zero_()
 
-    def broadcast_parameters(self, module_params):
-        """Make every rank's parameters equal rank 0's through the fusion buffers: pack, pull, unpack."""
+    def broadcast_parameters(self, module_params, src: int = 0):
+        """Make every rank's parameters equal rank ``src``'s through the fusion buffers: pack, pull, unpack."""
         if self.world == 1:
             return
         if not self.is_cuda:
             for p in module_params:
-                dist.broadcast(p.data, src=0, group=self.process_group)
+                dist.broadcast(p.data, src=src, group=self.process_group)
             return
         ctx = self.rt.ctx
         st = torch.cuda.current_stream(self.device).cuda_stream
         with torch.no_grad():
             for group in self.groups.values():
                 mine = [(p, ptr, nb) for b in self.buckets if b.group is group for p, ptr, nb in zip(b.params, b.ptrs, b.nbytes)]
-                if self.rank == 0:
+                if self.rank == src:
                     ctx.pack([p.data_ptr() for p, _, _ in mine], [ptr for _, ptr, _ in mine], [nb for _, _, nb in mine],
                              self.rt.use_bulk_pack, st)  # fmt: skip
                 nbytes = group.total_elems * group.elem_size
-                ctx.pull(group.segment.seg, 0, nbytes, group.flat.data_ptr(), 0, 0, 1, native.CH_USER, 0, st)
+                ctx.pull(group.segment.seg, 0, nbytes, group.flat.data_ptr(), 0, src, 1, native.CH_USER, 0, st)
                 for p, _, _ in mine:
                     if not p.is_contiguous():
                         raise ValueError("non-contiguous parameters are not supported by the B200 reducer")
@@ -658,7 +681,33 @@ class GradReducer:
         self._hooks = []
 
 
-class B200DataParallel(torch.nn.Module):
+class _B200JoinHook(JoinHook):
+    """What a rank does, once per iteration of the others, after it ran out of inputs inside ``torch``'s ``Join``
+    context (reference: accelerator.py:1299-1372 ``join_uneven_inputs`` -> torch ``_DDPJoinHook``): shadow the buffer
+    broadcast of the forward, learn whether the others reduce in this iteration, and if so shadow the reduction."""
+
+    def __init__(self, ddp, divide_by_initial_world_size: bool):
+        if not divide_by_initial_world_size:
+            raise NotImplementedError(
+                "divide_by_initial_world_size=False is not supported: the fused allreduce pre-divides by the world size"
+            )
+        self.ddp = ddp
+        super().__init__()
+
+    def main_hook(self):
+        ddp = self.ddp
+        if ddp._will_sync_buffers():
+            ddp._broadcast_buffers(ddp._find_common_rank(False))
+        should_sync = ddp._global_requires_backward_grad_sync(is_joined_rank=True)
+        ddp.require_forward_param_sync = should_sync
+        if should_sync:
+            ddp.reducer.shadow_backward()
+
+    def post_hook(self, is_last_joiner: bool):
+        self.ddp._sync_final_model(is_last_joiner)
+
+
+class B200DataParallel(torch.nn.Module, Joinable):
     """Drop-in for the ``DistributedDataParallel(model, device_ids=[local_rank], output_device=local_rank,
     **DistributedDataParallelKwargs.to_kwargs())`` call at ``accelerator.py:1892-1894``; exposes the
     attributes the reference and its tests read."""
@@ -667,6 +716,7 @@ class B200DataParallel(torch.nn.Module):
                  process_group=None, bucket_cap_mb=None, find_unused_parameters=False, check_reduction=False,
                  gradient_as_bucket_view=False, static_graph=False):  # fmt: skip
         super().__init__()
+        Joinable.__init__(self)
         params = [p for p in module.parameters() if p.requires_grad]
         if not params:
             raise RuntimeError("B200DataParallel is not needed when a module doesn't have any parameter that requires a gradient.")
@@ -739,14 +789,59 @@ class B200DataParallel(torch.nn.Module):
         else:
             self.reducer.set_user_hook(state, hook)
 
-    def _sync_buffers(self):
-        bufs = self._ddp_buffers
-        if not bufs or self.reducer.world == 1:
+    def _will_sync_buffers(self) -> bool:
+        return bool(self._ddp_buffers) and self.broadcast_buffers and self.require_forward_param_sync
+
+    def _broadcast_buffers(self, src: int):
+        if not self._ddp_buffers or self.reducer.world == 1:
             return
         from .utils.operations import broadcast
 
         with torch.no_grad():
-            broadcast(bufs, from_process=0)
+            broadcast(self._ddp_buffers, from_process=src)
+
+    def _sync_buffers(self):
+        # inside torch's Join context rank 0 may already have run out of data: agree on a rank that is still
+        # training (torch distributed.py:2214-2231)
+        self._broadcast_buffers(self._find_common_rank(True) if self._join_config.enable else 0)
+
+    # ---- uneven inputs: torch.distributed.algorithms.Join protocol ----
+    def join_hook(self, **kwargs):
+        return _B200JoinHook(self, divide_by_initial_world_size=kwargs.get("divide_by_initial_world_size", True))
+
+    @property
+    def join_device(self):
+        return self.reducer.device
+
+    @property
+    def join_process_group(self):
+        return self.process_group if self.process_group is not None else dist.group.WORLD
+
+    def _find_common_rank(self, candidate: bool) -> int:
+        """The largest rank for which ``candidate`` holds (one MAX allreduce, like torch's ``_find_common_rank``)."""
+        t = torch.tensor([self.reducer.rank if candidate else -1], device=self.reducer.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.process_group)
+        rank = int(t.item())
+        if rank == -1:
+            raise ValueError("no rank qualifies as the authoritative copy: every rank joined at once?")
+        return rank
+
+    def _global_requires_backward_grad_sync(self, is_joined_rank: bool):
+        """Ranks still training announce whether their coming backward reduces; joined ranks listen."""
+        flag = torch.ones(1, device=self.reducer.device) if (not is_joined_rank and self.require_backward_grad_sync) \
+            else torch.zeros(1, device=self.reducer.device)  # fmt: skip
+        work = dist.all_reduce(flag, group=self.process_group, async_op=True)
+        if is_joined_rank:
+            work.wait()
+            return flag.item() != 0
+        return None
+
+    def _sync_final_model(self, is_last_joiner: bool):
+        """Leaving the Join context: everyone adopts the model of the rank that trained longest."""
+        src = self._find_common_rank(is_last_joiner)
+        self.reducer.broadcast_parameters(self.reducer.params, src=src)
+        if self.broadcast_buffers:
+            self._broadcast_buffers(src)
 
     def forward(self, *inputs, **kwargs):
         if self.device_ids:  # torch DDP moves inputs to its device (_pre_forward -> _to_kwargs)
@@ -759,8 +854,13 @@ class B200DataParallel(torch.nn.Module):
         # iff the PREVIOUS forward was a gradient-syncing one (require_forward_param_sync), whatever the train/eval
         # mode; the sync decision for the coming backward is latched here, from require_backward_grad_sync
         # 
-        if self._ddp_buffers and self.broadcast_buffers and self.require_forward_param_sync:
+        joining = self._join_config.enable
+        if joining:
+            Join.notify_join_context(self)  # "this rank is still training" (one allreduce per iteration)
+        if self._will_sync_buffers():
             self._sync_buffers()
+        if joining:
+            self._global_requires_backward_grad_sync(is_joined_rank=False)
         output = self.module(*inputs, **kwargs)
         will_sync = torch.is_grad_enabled() and self.require_backward_grad_sync
         self.require_forward_param_sync = will_sync

@@ -120,6 +120,14 @@ def main():
                 local_sgd.step()
             log[f"local_sgd_{step}"] = ser(acc.unwrap_model(model).weight)
 
+    import warnings
+
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter("always")
+        with acc.join_uneven_inputs([model], even_batches=False):
+            pass
+    log["join_uneven_inputs_on_cpu"] = sorted({str(w.message) for w in caught if "Joining uneven" in str(w.message)})
+
     @acc.on_local_process(local_process_index=0)
     def only_local0():
         return "ran"

@@ -48,3 +48,11 @@ def test_differential_against_torch_ddp(seed):
     tied weights and BatchNorm buffers: gradients AND buffers bit-equal to torch DistributedDataParallel (gloo, N=2)."""
     out = run_distributed("dist_ddp_diff.py", 2, timeout=300, env={"DDP_DIFF_SEED": str(seed)})
     assert out.count("DDP_DIFF_OK") == 2, out[-3000:]
+
+
+@pytest.mark.parametrize("world,find_unused", [(2, "0"), (2, "1"), (4, "0")])
+def test_join_uneven_inputs_matches_torch_ddp(world, find_unused):
+    """torch's Join context (behind the reference's join_uneven_inputs): ranks train 3+2r iterations, early finishers
+    shadow the collectives; parameters after every step and the final synced model equal torch DDP's."""
+    out = run_distributed("dist_join.py", world, timeout=300, env={"JOIN_FIND_UNUSED": find_unused})
+    assert out.count("JOIN_OK") == world, out[-3000:]
