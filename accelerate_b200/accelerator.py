@@ -118,10 +118,11 @@ class Accelerator:
         # ---- mixed precision: fp16 gets a (fused) GradScaler, bf16 none (accelerator.py:564-596) ----
         self.scaler = None
         self.native_amp = False
-        if self.state.mixed_precision == "fp16":
+        if self.state.mixed_precision == "fp16" and self.device.type != "cpu":
+            # (on a CPU device the reference silently trains in full precision: accelerator.py:564-567)
             self.native_amp = True
             if self.device.type != "cuda":
-                raise ValueError("fp16 mixed precision requires a GPU.")
+                raise ValueError(f"fp16 mixed precision requires a device in ('cuda',) (not {self.device.type!r}).")
             from .scaler import FusedGradScaler
 
             self.scaler = FusedGradScaler("cuda", **(self.scaler_handler.to_kwargs() if self.scaler_handler else {}))

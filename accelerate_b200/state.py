@@ -176,11 +176,25 @@ class PartialState(_Borg):
 
         width = per + (1 if extra > 0 else 0)  # the longest share
 
+        def take_dataset(data):
+            # a Hugging Face `datasets.Dataset` is split by row selection (state.py:498-511); anything else passes through
+            try:
+                from datasets import Dataset
+            except ImportError:
+                return data
+            if not isinstance(data, Dataset):
+                return data
+            lo, hi = min(start, len(data) - 1), min(end, len(data))
+            rows = list(range(lo, hi))
+            if apply_padding:
+                rows += [hi - 1] * (width - len(rows))
+            return data.select(rows)
+
         def take(seq):
             # semantics of state.py:477-492: a rank past the end still gets the last element; lists are padded with
             # the share's own last element, tensors with the input's last row through pad_across_processes (a collective)
             if not isinstance(seq, (list, tuple, torch.Tensor)):
-                return seq
+                return take_dataset(seq)
             part = seq[-1:] if start >= len(seq) else seq[start:end]
             if apply_padding:
                 if isinstance(part, torch.Tensor):
@@ -306,6 +320,12 @@ class AcceleratorState(_Borg):
     def __getattr__(self, name):
         if name.startswith("__"):
             raise AttributeError(name)
+        if not AcceleratorState._shared and name in PartialState._known_attrs:
+            # the shared state was wiped under a live Accelerator (state.py:1221-1231)
+            raise AttributeError(
+                f"`AcceleratorState` object has no attribute `{name}`. This happens if `AcceleratorState._reset_state()` "
+                "was called and an `Accelerator` or `PartialState` was not reinitialized."
+            )
         partial = PartialState._shared
         if name in partial:
             return partial[name]

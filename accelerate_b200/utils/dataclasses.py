@@ -52,11 +52,23 @@ class BaseEnum(enum.Enum, metaclass=_ContainsMeta):
 
 
 class DistributedType(str, enum.Enum):
-    """Only the values this build can take: no distributed run, multi-GPU (CUDA) and multi-CPU (gloo; host-logic tests)."""
+    """This build only ever takes NO, MULTI_GPU (CUDA) and MULTI_CPU (gloo; host-logic tests); the remaining members
+    of the reference's enum (dataclasses.py:606-636) exist so that scripts comparing against them keep working."""
 
     NO = "NO"
     MULTI_CPU = "MULTI_CPU"
     MULTI_GPU = "MULTI_GPU"
+    MULTI_NPU = "MULTI_NPU"
+    MULTI_MLU = "MULTI_MLU"
+    MULTI_SDAA = "MULTI_SDAA"
+    MULTI_MUSA = "MULTI_MUSA"
+    MULTI_XPU = "MULTI_XPU"
+    DEEPSPEED = "DEEPSPEED"
+    FSDP = "FSDP"
+    XLA = "XLA"
+    MEGATRON_LM = "MEGATRON_LM"
+    MULTI_HPU = "MULTI_HPU"
+    MULTI_NEURON = "MULTI_NEURON"
 
 
 class PrecisionType(str, BaseEnum):

@@ -252,6 +252,38 @@ def gather_object(object: Any):
     return [item for part in parts for item in part]
 
 
+# dtype codes of the shape message (operations.py:536-549)
+TENSOR_TYPE_TO_INT = {
+    torch.float: 1, torch.double: 2, torch.half: 3, torch.bfloat16: 4, torch.uint8: 5, torch.int8: 6, torch.int16: 7,
+    torch.int32: 8, torch.int64: 9, torch.bool: 10,
+}  # fmt: skip
+TENSOR_INT_TO_DTYPE = {v: k for k, v in TENSOR_TYPE_TO_INT.items()}
+
+
+def gather_tensor_shape(tensor):
+    """Shape and dtype code of a tensor that exists on ONE process only (``None`` elsewhere), learnt by all through a
+    sum-reduction of a small zero-initialised message (operations.py:552-574).  Returns ``(dims, dtype_code)``; as in
+    the reference, dimensions of size 0 cannot be represented."""
+    state = PartialState()
+    message = torch.zeros(64, dtype=torch.int, device=state.device)
+    if tensor is not None:
+        dims = list(tensor.shape) + [TENSOR_TYPE_TO_INT[tensor.dtype]]
+        message[: len(dims)] = torch.tensor(dims, dtype=torch.int)
+    message = reduce(message, reduction="sum")
+    message = message[message.nonzero()]
+    return message[:-1], int(message[-1:][0])
+
+
+def copy_tensor_to_devices(tensor=None) -> torch.Tensor:
+    """Give every process a copy of a tensor only one of them holds, without the others knowing its shape
+    (operations.py:577-591): shape message, then a sum-reduction against zeros."""
+    state = PartialState()
+    shape, dtype = gather_tensor_shape(tensor)
+    if tensor is None:
+        tensor = torch.zeros([int(d) for d in shape.flatten().tolist()], dtype=TENSOR_INT_TO_DTYPE[dtype]).to(state.device)
+    return reduce(tensor, reduction="sum")
+
+
 @verify_operation
 def broadcast(tensor, from_process: int = 0):
     """In-place broadcast of every leaf from ``from_process`` (operations.py:594-613)."""
