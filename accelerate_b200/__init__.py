@@ -9,12 +9,14 @@ __version__ = "0.1.0"
 
 from .accelerator import Accelerator
 from .data_loader import skip_first_batches
+from .launchers import debug_launcher
 from .local_sgd import LocalSGD
 from .optimizer import AcceleratedOptimizer
 from .reducer import B200DataParallel
 from .scheduler import AcceleratedScheduler
 from .state import AcceleratorState, GradientState, PartialState
 from .utils import (
+    synchronize_rng_states,
     AutocastKwargs,
     DataLoaderConfiguration,
     DDPCommunicationHookType,

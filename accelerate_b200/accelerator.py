@@ -803,15 +803,49 @@ class Accelerator:
             load_custom_state(obj, input_dir, i)
         self.wait_for_everyone()
 
-    def save_model(self, model, save_directory, safe_serialization: bool = True):
-        """Unwrapped weights in one file (``model.safetensors`` / ``pytorch_model.bin``), main process only."""
+    def save_model(self, model, save_directory, max_shard_size="10GB", safe_serialization: bool = True):
+        """Unwrapped weights for re-loading outside a training run (accelerator.py:3433-3546): ``model.safetensors`` /
+        ``pytorch_model.bin``, or — above ``max_shard_size`` — numbered shard files plus an ``*.index.json`` weight map,
+        the layout ``transformers`` / ``load_checkpoint_in_model`` read.  Main process writes."""
+        import json
+        import re
         from pathlib import Path
+
+        from huggingface_hub import split_torch_state_dict_into_shards
 
         from .checkpointing import MODEL_NAME, SAFE_MODEL_NAME, _write
 
+        if os.path.isfile(save_directory):
+            raise ValueError(f"Provided path ({save_directory}) should be a directory, not a file")
+        if any(p.device == torch.device("meta") for p in model.parameters()):
+            raise RuntimeError("You can't save the model since some parameters are on the meta device.")
+        state_dict = self.get_state_dict(model)
         os.makedirs(save_directory, exist_ok=True)
-        name = f"{SAFE_MODEL_NAME}.safetensors" if safe_serialization else f"{MODEL_NAME}.bin"
-        _write(self.get_state_dict(model), Path(save_directory) / name, self.is_main_process, safe=safe_serialization)
+        if safe_serialization:  # one name per storage (tied weights), as safetensors requires
+            seen, unique = set(), {}
+            for name, t in state_dict.items():
+                key = (t.untyped_storage().data_ptr(), t.storage_offset(), tuple(t.shape)) if t.numel() else name
+                if key not in seen:
+                    seen.add(key)
+                    unique[name] = t
+            state_dict = unique
+        stem, ext = (SAFE_MODEL_NAME, "safetensors") if safe_serialization else (MODEL_NAME, "bin")
+        split = split_torch_state_dict_into_shards(
+            state_dict, filename_pattern=stem + "{suffix}." + ext, max_shard_size=max_shard_size
+        )
+        # shard files of an earlier save that this one does not overwrite would poison a later load
+        shard_name = re.compile(re.escape(stem) + r"-\d{5}-of-\d{5}\." + ext)
+        if self.is_main_process:
+            for filename in os.listdir(save_directory):
+                if shard_name.fullmatch(filename) and filename not in split.filename_to_tensors:
+                    os.remove(os.path.join(save_directory, filename))
+        for filename, names in split.filename_to_tensors.items():
+            shard = {name: state_dict[name] for name in names}
+            _write(shard, Path(save_directory) / filename, self.is_main_process, safe=safe_serialization)
+        if split.is_sharded and self.is_main_process:
+            index = {"metadata": split.metadata, "weight_map": split.tensor_to_filename}
+            with open(os.path.join(save_directory, f"{stem}.{ext}.index.json"), "w", encoding="utf-8") as f:
+                f.write(json.dumps(index, indent=2, sort_keys=True) + "\n")
         self.wait_for_everyone()
 
     def end_training(self):

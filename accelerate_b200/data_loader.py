@@ -217,11 +217,23 @@ class IterableDatasetShard(IterableDataset):
         yield from group[lo : lo + share]
 
 
-class _EpochBookkeeping:
-    """end_of_dataloader / remainder tracking shared by the two loader classes (data_loader.py:365-407)."""
+class _InstanceItself:
+    """``loader.base_dataloader``: the reference wraps a ``DataLoader`` (``DataLoaderAdapter``); these classes ARE one.
+    An instance-only attribute there, so class-level access raises."""
+
+    def __get__(self, obj, owner=None):
+        if obj is None:
+            raise AttributeError("base_dataloader")
+        return obj
+
+
+class DataLoaderStateMixin:
+    """end_of_dataloader / remainder tracking shared by the loader classes (data_loader.py:365-407)."""
 
     end_of_dataloader = False
     remainder = -1
+
+    base_dataloader = _InstanceItself()
 
     def reset(self):
         self.end_of_dataloader = False
@@ -252,7 +264,7 @@ def _forward_set_epoch(loader, epoch: int):
         loader.dataset.set_epoch(epoch)
 
 
-class DataLoaderShard(DataLoader, _EpochBookkeeping):
+class DataLoaderShard(DataLoader, DataLoaderStateMixin):
     """A DataLoader that (1) synchronises RNGs at epoch start, (2) puts batches on the device one
     batch ahead, (3) flags the last batch in ``GradientState`` *before* yielding it."""
 
@@ -327,7 +339,7 @@ class DataLoaderShard(DataLoader, _EpochBookkeeping):
                 self.batch_sampler.batch_sampler.sampler = sampler
 
 
-class DataLoaderDispatcher(DataLoader, _EpochBookkeeping):
+class DataLoaderDispatcher(DataLoader, DataLoaderStateMixin):
     """Rank 0 reads the data; every step it announces the batch's structure (object broadcast) and
     then its tensors (P2P broadcast kernel on CUDA); each rank keeps its slice."""
 
@@ -447,6 +459,14 @@ class DataLoaderDispatcher(DataLoader, _EpochBookkeeping):
             self.batch_sampler.sampler = sampler
 
 
+def _is_hf_iterable(dataset) -> bool:
+    try:
+        from datasets import IterableDataset as HFIterableDataset
+    except ImportError:
+        return False
+    return isinstance(dataset, HFIterableDataset)
+
+
 def get_sampler(dataloader):
     if isinstance(dataloader.sampler, BatchSampler):
         return getattr(dataloader.sampler, "sampler", None)
@@ -497,7 +517,11 @@ def prepare_data_loader(dataloader, device=None, num_processes=None, process_ind
         )
 
     if num_processes != 1 and not dispatch_batches:
-        if iterable:
+        if _is_hf_iterable(dataset) and not split_batches and dataset.n_shards >= num_processes:
+            # a Hugging Face streaming dataset with enough shards is split natively, whole shards per process
+            # (data_loader.py:1214-1221); fewer shards fall back to striding through the stream below
+            dataset = dataset.shard(num_shards=num_processes, index=process_index)
+        elif iterable:
             if getattr(dataset, "generator", None) is not None:
                 synchronized_generator = dataset.generator
             dataset = IterableDatasetShard(
@@ -570,7 +594,7 @@ class SkipBatchSampler(BatchSampler):
         return len(self.batch_sampler) - self.skip_batches
 
 
-class SkipDataLoader(DataLoader, _EpochBookkeeping):
+class SkipDataLoader(DataLoader, DataLoaderStateMixin):
     def __init__(self, dataset, skip_batches=0, **kwargs):
         super().__init__(dataset, **kwargs)
         self.skip_batches = skip_batches

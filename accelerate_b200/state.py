@@ -93,7 +93,12 @@ class PartialState(_Borg):
             self.backend = None
             self.num_processes = 1
             self.process_index = self.local_process_index = 0
-            self.device = torch.device("cuda", torch.cuda.current_device()) if use_cuda else torch.device("cpu")
+            env_device = os.environ.get("ACCELERATE_TORCH_DEVICE")  # explicit override (state.py:182-183)
+            if env_device is not None:
+                self.device = torch.device(env_device)
+                use_cuda = self.device.type == "cuda"
+            else:
+                self.device = torch.device("cuda", torch.cuda.current_device()) if use_cuda else torch.device("cpu")
             if use_cuda:
                 torch.cuda.set_device(self.device)
 
@@ -329,7 +334,10 @@ class AcceleratorState(_Borg):
         partial = PartialState._shared
         if name in partial:
             return partial[name]
-        return getattr(PartialState(), name)
+        try:
+            return getattr(PartialState(), name)
+        except AttributeError:
+            raise AttributeError(f"'AcceleratorState' object has no attribute '{name}'") from None
 
     @classmethod
     def _reset_state(cls, reset_partial_state: bool = False):

@@ -63,3 +63,40 @@ def patch_environment(**kwargs):
                 os.environ.pop(key, None)
             else:
                 os.environ[key] = old
+
+
+def purge_accelerate_environment(func_or_cls):
+    """Decorator for tests (functions, ``unittest.TestCase`` or plain pytest classes, subclasses included): whatever
+    ``ACCELERATE_*`` variables a test sets are removed — and pre-existing ones restored — when it returns, so tests do
+    not leak configuration into each other (``utils/environment.py:405-474``)."""
+    import functools
+
+    def guarded(func):
+        @functools.wraps(func)
+        def wrapper(*args, **kwargs):
+            before = {k: v for k, v in os.environ.items() if k.startswith("ACCELERATE_")}
+            try:
+                return func(*args, **kwargs)
+            finally:
+                for key in [k for k in os.environ if k.startswith("ACCELERATE_")]:
+                    if key in before:
+                        os.environ[key] = before[key]
+                    else:
+                        del os.environ[key]
+
+        wrapper._accelerate_is_purged_environment_wrapped = True
+        return wrapper
+
+    if not isinstance(func_or_cls, type):
+        return guarded(func_or_cls)
+
+    def wrap_tests(cls):
+        for name in dir(cls):
+            method = getattr(cls, name)
+            if name.startswith("test") and callable(method) and not hasattr(method, "_accelerate_is_purged_environment_wrapped"):
+                setattr(cls, name, guarded(method))
+        return cls
+
+    wrap_tests(func_or_cls)
+    func_or_cls.__init_subclass__ = classmethod(lambda cls, **kw: wrap_tests(cls))
+    return func_or_cls
