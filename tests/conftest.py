@@ -24,15 +24,26 @@ def _fresh_state():
     # PartialState (process group / native runtime) survives: one per test process
 
 
+import threading  # noqa: E402
+
+_PORT_LOCK = threading.Lock()
+_PORTS_HANDED_OUT = set()
+
+
 def run_distributed(script, nproc, *args, env=None, timeout=600):
     """torchrun a script under tests/scripts with `nproc` ranks on this node; returns combined output."""
     import socket
     import subprocess
 
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    port = s.getsockname()[1]
-    s.close()
+    with _PORT_LOCK:  # concurrent launches (thread pools in the differential tests) must not be handed the same port
+        while True:
+            s = socket.socket()
+            s.bind(("127.0.0.1", 0))
+            port = s.getsockname()[1]
+            s.close()
+            if port not in _PORTS_HANDED_OUT:
+                _PORTS_HANDED_OUT.add(port)
+                break
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
            "--master-addr", "127.0.0.1", "--master-port", str(port),
            os.path.join(ROOT, "tests", "scripts", script), *args]  # fmt: skip

@@ -13,7 +13,7 @@ REF = "/root/reference/src"
 pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
 
 
-def test_training_loop_matches_the_reference(tmp_path):
+def check_training_loop(tmp_path):
     outs = {}
     for impl in ("reference", "ours"):
         base = str(tmp_path / impl)
@@ -33,8 +33,7 @@ def test_training_loop_matches_the_reference(tmp_path):
             assert ref["final_state_sha256"] == ours["final_state_sha256"], (variant, r)
 
 
-@pytest.mark.parametrize("world", [3])
-def test_collective_and_process_control_api_matches_the_reference(tmp_path, world):
+def check_api(tmp_path, world=3):
     outs = {}
     for impl in ("reference", "ours"):
         base = str(tmp_path / impl)
@@ -51,8 +50,7 @@ def test_collective_and_process_control_api_matches_the_reference(tmp_path, worl
             assert ref[key] == ours[key], (world, r, key, ref[key], ours[key])
 
 
-@pytest.mark.parametrize("world", [3])
-def test_prepared_dataloaders_match_the_reference(tmp_path, world):
+def check_dataloaders(tmp_path, world=3):
     """~130 (length, batch size, drop_last, split_batches, shard/dispatch/iterable, shuffle, even_batches) cases: every
     batch on every rank over two epochs, end_of_dataloader/remainder, gather_for_metrics, len, skip_first_batches."""
     outs = {}
@@ -68,8 +66,23 @@ def test_prepared_dataloaders_match_the_reference(tmp_path, world):
             assert a == b, (world, r, a["cfg"])
 
 
-def test_mid_epoch_resume_is_interchangeable_with_the_reference(tmp_path):
+def check_resume(tmp_path):
     """save_state in the middle of an epoch with either library, resume (load_state + skip_first_batches) with either
     library, 2 ranks: all four combinations end with the weights of an uninterrupted run; same files on disk."""
     out = run_distributed("dist_resume_diff.py", 2, "--dir", str(tmp_path), env={"PYTHONDONTWRITEBYTECODE": "1"}, timeout=600)
     assert out.count("RESUME_OK") == 2, out[-3000:]
+
+
+def test_same_script_under_both_libraries(tmp_path):
+    """The four differential checks above, run concurrently (each launches its own torchrun groups):
+    training loop (7 variants, 2 ranks), collective / process-control / checkpoint API (3 ranks), prepared dataloaders
+    (~70 configurations, 3 ranks), mid-epoch save/resume across the libraries (2 ranks)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    checks = {"training_loop": check_training_loop, "api": check_api, "dataloaders": check_dataloaders, "resume": check_resume}
+    for name in checks:
+        (tmp_path / name).mkdir()
+    with ThreadPoolExecutor(max_workers=4) as pool:
+        futures = {name: pool.submit(fn, tmp_path / name) for name, fn in checks.items()}
+    errors = {name: f.exception() for name, f in futures.items() if f.exception() is not None}
+    assert not errors, "\n\n".join(f"{name}: {err!r}" for name, err in errors.items())

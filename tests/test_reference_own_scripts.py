@@ -22,33 +22,25 @@ def launch(script, world):
     assert out.count(f"REFERENCE_SCRIPT_OK {script}") == world, out[-3000:]
 
 
-@pytest.mark.parametrize("world", [2])
-def test_reference_test_sync(world):
-    """test_sync.py: mean-of-gradients, no_sync, accumulate, dataloader-driven sync, schedulers."""
-    launch("test_sync.py", world)
+def _single_process(script):
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "refshim", "run_reference_script.py"), script],
+                         env=dict(os.environ, **ENV), capture_output=True, text=True, timeout=600, cwd=ROOT)  # fmt: skip
+    assert res.returncode == 0 and f"REFERENCE_SCRIPT_OK {script}" in res.stdout, res.stderr[-3000:]
 
 
-@pytest.mark.parametrize("world", [4])
-def test_reference_test_ops(world):
-    """test_ops.py: gather / gather_object / broadcast / pad_across_processes / reduce, debug-mode shape checks."""
-    launch("test_ops.py", world)
+def test_reference_distributed_scripts():
+    """test_sync.py (mean-of-gradients, no_sync, accumulate, schedulers; 2 ranks), test_ops.py (gather / gather_object /
+    broadcast / pad / reduce, debug-mode shape checks; 4 ranks), test_script.py (process control, RNG sync, dataloader
+    preparation, training_check incl. bf16 and fp16-on-CPU, splits; 2 ranks and 1 process), test_distributed_data_loop.py
+    (2 ranks) — run concurrently."""
+    from concurrent.futures import ThreadPoolExecutor
 
-
-@pytest.mark.parametrize("world", [2])
-def test_reference_test_script(world):
-    """test_script.py: process control, RNG sync, dataloader preparation, training_check (bf16 / fp16-on-CPU), splits."""
-    launch("test_script.py", world)
-
-
-def test_reference_test_distributed_data_loop():
-    launch("test_distributed_data_loop.py", 2)
-
-
-def test_reference_scripts_single_process():
-    for script in ("test_script.py",):
-        res = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "refshim", "run_reference_script.py"), script],
-                             env=dict(os.environ, **ENV), capture_output=True, text=True, timeout=600, cwd=ROOT)  # fmt: skip
-        assert res.returncode == 0 and f"REFERENCE_SCRIPT_OK {script}" in res.stdout, res.stderr[-3000:]
+    jobs = [(launch, "test_sync.py", 2), (launch, "test_ops.py", 4), (launch, "test_script.py", 2),
+            (launch, "test_distributed_data_loop.py", 2), (_single_process, "test_script.py")]  # fmt: skip
+    with ThreadPoolExecutor(max_workers=3) as pool:
+        futures = [(job[1:], pool.submit(job[0], *job[1:])) for job in jobs]
+    errors = [(what, f.exception()) for what, f in futures if f.exception() is not None]
+    assert not errors, "\n\n".join(f"{what}: {err!r}" for what, err in errors)
 
 
 # ---- the reference's unit-test FILES (reference/tests/*.py) under pytest, same import alias --------------------------
