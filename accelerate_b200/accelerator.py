@@ -455,6 +455,7 @@ class Accelerator:
             dispatch_batches=self.dispatch_batches, even_batches=self.even_batches,
             slice_fn_for_dispatch=slice_fn_for_dispatch, use_seedable_sampler=self.use_seedable_sampler,
             data_seed=self.dataloader_config.data_seed, non_blocking=self.non_blocking,
+            use_stateful_dataloader=self.use_stateful_dataloader,
         )  # fmt: skip
         self._dataloaders.append(prepared)
         return prepared

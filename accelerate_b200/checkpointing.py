@@ -72,6 +72,9 @@ def save_accelerator_state(output_dir, model_states, optimizers, schedulers, dat
             sampler = dl.get_sampler()
             if isinstance(sampler, SeedableRandomSampler):
                 _write(sampler, out / _numbered(SAMPLER_NAME, i, "bin"), writer)
+        if getattr(dl, "use_stateful_dataloader", False):
+            # resume point inside the epoch; like the reference (checkpointing.py:141-145) EVERY process writes it
+            _write(dl.state_dict(), out / _numbered("dl_state_dict", i, "bin"), True)
     if scaler is not None:
         _write(scaler.state_dict(), out / SCALER_NAME, writer)
     # every process keeps its own RNG streams
@@ -126,6 +129,10 @@ def load_accelerator_state(input_dir, models, optimizers, schedulers, dataloader
     for i, dl in enumerate(dataloaders):
         if isinstance(dl.dataset, IterableDatasetShard) and isinstance(dl.get_sampler(), SeedableRandomSampler):
             dl.set_sampler(_read(src / _numbered(SAMPLER_NAME, i, "bin"), weights_only=False))
+        if getattr(dl, "use_stateful_dataloader", False):
+            state_file = src / _numbered("dl_state_dict", i, "bin")
+            if state_file.exists():
+                dl.load_state_dict(_read(state_file, weights_only=False))
     if scaler is not None:
         scaler.load_state_dict(_read(src / SCALER_NAME))
     overrides = {}

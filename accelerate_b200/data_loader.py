@@ -21,6 +21,7 @@ import torch
 from torch.utils.data import BatchSampler, DataLoader, IterableDataset, RandomSampler
 
 from .state import GradientState, PartialState
+from .utils.dataclasses import DistributedType
 from .utils.operations import (
     broadcast,
     broadcast_object_list,
@@ -217,6 +218,71 @@ class IterableDatasetShard(IterableDataset):
         yield from group[lo : lo + share]
 
 
+_STATEFUL_VARIANTS: dict = {}
+
+
+def _stateful_base():
+    """torchdata's drop-in ``StatefulDataLoader`` (mid-epoch ``state_dict`` / ``load_state_dict``)."""
+    try:
+        from torchdata.stateful_dataloader import StatefulDataLoader
+    except ImportError as err:
+        raise ImportError(
+            "StatefulDataLoader is not available. Please install torchdata version 0.8.0 or higher to use it."
+        ) from err
+    return StatefulDataLoader
+
+
+class _StatefulSupport:
+    """``use_stateful_dataloader=True`` (data_loader.py:408-499): the loader is built on torchdata's
+    ``StatefulDataLoader`` instead of ``DataLoader`` and carries a ``state_dict`` that resumes exactly after the last
+    batch it has YIELDED — these loaders fetch one batch ahead of what they hand out, so the underlying iterator's
+    state is snapshotted before each look-ahead fetch.  The stateful flavour of a class is a subclass created on first
+    use (``isinstance`` holds for the class itself and for ``StatefulDataLoader``)."""
+
+    use_stateful_dataloader = False
+
+    def __new__(cls, *args, **kwargs):
+        if kwargs.get("use_stateful_dataloader"):
+            base = _stateful_base()
+            if not issubclass(cls, base):
+                if cls not in _STATEFUL_VARIANTS:
+                    _STATEFUL_VARIANTS[cls] = type(cls.__name__, (cls, base), {"__module__": cls.__module__})
+                cls = _STATEFUL_VARIANTS[cls]
+        return super().__new__(cls)
+
+    def _start_state_tracking(self, use_stateful_dataloader: bool):
+        self.use_stateful_dataloader = bool(use_stateful_dataloader)
+        if self.use_stateful_dataloader:
+            self.dl_state_dict = super().state_dict()
+
+    def state_dict(self):
+        return self.dl_state_dict
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+
+    def adjust_state_dict_for_prefetch(self):
+        """In a distributed run every batch this process yields consumed ``num_processes`` batches of the underlying
+        sampler, and the snapshot is taken one of OUR batches early: the counters are ``num_processes - 1`` ahead."""
+        state = PartialState()
+        if state.distributed_type == DistributedType.NO:
+            return
+        ahead = state.num_processes - 1
+        sd = self.dl_state_dict
+        for key in ("_sampler_iter_yielded", "_num_yielded"):  # (absent with worker processes)
+            if sd.get(key, 0) > 0:
+                sd[key] -= ahead
+        inner = sd.get("_index_sampler_state")
+        if inner is not None and inner.get("samples_yielded", 0) > 0:
+            inner["samples_yielded"] -= self.batch_size * ahead
+
+    def _update_state_dict(self):
+        if self.use_stateful_dataloader:
+            self.dl_state_dict = super().state_dict()
+            self.adjust_state_dict_for_prefetch()
+            self.dl_state_dict["_iterator_finished"] = self.end_of_dataloader
+
+
 class _InstanceItself:
     """``loader.base_dataloader``: the reference wraps a ``DataLoader`` (``DataLoaderAdapter``); these classes ARE one.
     An instance-only attribute there, so class-level access raises."""
@@ -264,13 +330,13 @@ def _forward_set_epoch(loader, epoch: int):
         loader.dataset.set_epoch(epoch)
 
 
-class DataLoaderShard(DataLoader, DataLoaderStateMixin):
+class DataLoaderShard(_StatefulSupport, DataLoader, DataLoaderStateMixin):
     """A DataLoader that (1) synchronises RNGs at epoch start, (2) puts batches on the device one
     batch ahead, (3) flags the last batch in ``GradientState`` *before* yielding it."""
 
     def __init__(self, dataset, device=None, rng_types=None, synchronized_generator=None, skip_batches=0,
-                 _drop_last: bool = False, _non_blocking: bool = False, **kwargs):  # fmt: skip
-        kwargs.pop("use_stateful_dataloader", None)
+                 _drop_last: bool = False, _non_blocking: bool = False, use_stateful_dataloader: bool = False,
+                 **kwargs):  # fmt: skip
         kwargs.pop("torch_device_mesh", None)
         super().__init__(dataset, **kwargs)
         self.device = device
@@ -281,6 +347,12 @@ class DataLoaderShard(DataLoader, DataLoaderStateMixin):
         self._drop_last = _drop_last
         self._non_blocking = _non_blocking
         self.iteration = 0
+        self._start_state_tracking(use_stateful_dataloader)
+
+    def adjust_state_dict_for_prefetch(self):
+        """Nothing to correct here: every process iterates its own shard and the snapshot is taken before the
+        look-ahead fetch, so the counters already equal the batches handed to the user (data_loader.py:560-566).
+        The dispatcher, whose rank 0 draws ``num_processes`` batches per step, keeps the default correction."""
 
     def __iter__(self):
         if self.rng_types is not None:
@@ -297,10 +369,12 @@ class DataLoaderShard(DataLoader, DataLoaderStateMixin):
         while True:
             if self.device is not None:
                 held = send_to_device(held, self.device, non_blocking=self._non_blocking)
+            self._update_state_dict()  # resume point = right after `held`
             try:
                 upcoming = next(source)
             except StopIteration:
                 self.end_of_dataloader = True
+                self._update_state_dict()
                 if index >= self.skip_batches:
                     yield held
                 break
@@ -339,13 +413,12 @@ class DataLoaderShard(DataLoader, DataLoaderStateMixin):
                 self.batch_sampler.batch_sampler.sampler = sampler
 
 
-class DataLoaderDispatcher(DataLoader, DataLoaderStateMixin):
+class DataLoaderDispatcher(_StatefulSupport, DataLoader, DataLoaderStateMixin):
     """Rank 0 reads the data; every step it announces the batch's structure (object broadcast) and
     then its tensors (P2P broadcast kernel on CUDA); each rank keeps its slice."""
 
     def __init__(self, dataset, split_batches: bool = False, skip_batches=0, _drop_last: bool = False,
-                 _non_blocking: bool = False, slice_fn=None, **kwargs):  # fmt: skip
-        kwargs.pop("use_stateful_dataloader", None)
+                 _non_blocking: bool = False, slice_fn=None, use_stateful_dataloader: bool = False, **kwargs):  # fmt: skip
         kwargs.pop("torch_device_mesh", None)
         shuffle = False
         super().__init__(dataset, **kwargs)
@@ -359,6 +432,7 @@ class DataLoaderDispatcher(DataLoader, DataLoaderStateMixin):
         self.skip_batches = skip_batches
         self.slice_fn = slice_tensors if slice_fn is None else slice_fn
         self.iteration = 0
+        self._start_state_tracking(use_stateful_dataloader)
 
     def _fetch(self, source):
         """-> (batch, structure, exhausted).  Only rank 0 touches ``source``; one object broadcast tells
@@ -368,9 +442,11 @@ class DataLoaderDispatcher(DataLoader, DataLoaderStateMixin):
             pieces, exhausted = [], False
             try:
                 if self.split_batches:
+                    self._update_state_dict()
                     batch = next(source)
                 else:
                     for _ in range(self.state.num_processes):
+                        self._update_state_dict()
                         pieces.append(next(source))
             except StopIteration:
                 exhausted = True
@@ -416,6 +492,7 @@ class DataLoaderDispatcher(DataLoader, DataLoaderStateMixin):
             mine = self.slice_fn(batch, window, process_index=rank, num_processes=world)
             if last:
                 self.end_of_dataloader = True
+                self._update_state_dict()
                 self.remainder = observed
             if index >= self.skip_batches:
                 yield mine
@@ -479,7 +556,7 @@ def prepare_data_loader(dataloader, device=None, num_processes=None, process_ind
                         use_stateful_dataloader=False, torch_device_mesh=None):  # fmt: skip
     """Rebuild ``dataloader`` so that this process only sees its share (data_loader.py:1006-1319)."""
     if use_stateful_dataloader:
-        raise NotImplementedError("torchdata StatefulDataLoader is not supported by this build")
+        _stateful_base()  # fail early, with the reference's message, when torchdata is missing
     if dispatch_batches is None:
         dispatch_batches = put_on_device and isinstance(dataloader.dataset, IterableDataset)
     if dispatch_batches and not put_on_device:
@@ -555,19 +632,20 @@ def prepare_data_loader(dataloader, device=None, num_processes=None, process_ind
         kwargs.pop("generator")
         new = DataLoaderDispatcher(
             dataset, split_batches=split_batches, batch_sampler=new_batch_sampler, _drop_last=dataloader.drop_last,
-            _non_blocking=non_blocking, slice_fn=slice_fn_for_dispatch, **kwargs,
+            _non_blocking=non_blocking, slice_fn=slice_fn_for_dispatch, use_stateful_dataloader=use_stateful_dataloader,
+            **kwargs,
         )  # fmt: skip
     elif sampler_is_batch_sampler:
         new = DataLoaderShard(
             dataset, device=target, sampler=new_batch_sampler, batch_size=dataloader.batch_size, rng_types=rng_types,
             synchronized_generator=synchronized_generator, _drop_last=dataloader.drop_last, _non_blocking=non_blocking,
-            **kwargs,
+            use_stateful_dataloader=use_stateful_dataloader, **kwargs,
         )  # fmt: skip
     else:
         new = DataLoaderShard(
             dataset, device=target, batch_sampler=new_batch_sampler, rng_types=rng_types,
             synchronized_generator=synchronized_generator, _drop_last=dataloader.drop_last, _non_blocking=non_blocking,
-            **kwargs,
+            use_stateful_dataloader=use_stateful_dataloader, **kwargs,
         )  # fmt: skip
     if isinstance(sampler, SeedableRandomSampler) and use_seedable_sampler:
         new.set_sampler(sampler)
@@ -594,17 +672,19 @@ class SkipBatchSampler(BatchSampler):
         return len(self.batch_sampler) - self.skip_batches
 
 
-class SkipDataLoader(DataLoader, DataLoaderStateMixin):
-    def __init__(self, dataset, skip_batches=0, **kwargs):
+class SkipDataLoader(_StatefulSupport, DataLoader, DataLoaderStateMixin):
+    def __init__(self, dataset, skip_batches=0, use_stateful_dataloader: bool = False, **kwargs):
         super().__init__(dataset, **kwargs)
         self.skip_batches = skip_batches
         self.gradient_state = GradientState()
         self._drop_last = kwargs.get("drop_last", False)
+        self._start_state_tracking(use_stateful_dataloader)
 
     def __iter__(self):
         self.begin()
         for k, batch in enumerate(super().__iter__()):
             if k >= self.skip_batches:
+                self._update_state_dict()
                 yield batch
         self.end()
 

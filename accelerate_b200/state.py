@@ -44,6 +44,7 @@ class _Borg:
 
 class PartialState(_Borg):
     _shared: dict = {}
+    _shared_state = _shared  # the reference's name for the same dict (tests and user code peek at it)
     _known_attrs = [
         "_cpu", "backend", "device", "debug", "distributed_type", "fork_launched", "local_process_index",
         "num_processes", "process_index", "runtime",
@@ -283,6 +284,7 @@ class PartialState(_Borg):
 
 class AcceleratorState(_Borg):
     _shared: dict = {}
+    _shared_state = _shared  # the reference's name for the same dict (tests and user code peek at it)
 
     def __init__(self, mixed_precision: str = None, cpu: bool = False, _from_accelerator: bool = False, **kwargs):
         super().__init__()
@@ -350,6 +352,7 @@ class GradientState(_Borg):
     """``sync_gradients`` gates the reducer, the optimizer and the scheduler (state.py:1234-1374)."""
 
     _shared: dict = {}
+    _shared_state = _shared  # the reference's name for the same dict (tests and user code peek at it)
 
     def __init__(self, gradient_accumulation_plugin: GradientAccumulationPlugin | None = None):
         super().__init__()

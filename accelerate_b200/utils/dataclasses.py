@@ -194,10 +194,6 @@ class DataLoaderConfiguration:
     non_blocking: bool = False
     use_stateful_dataloader: bool = False
 
-    def __post_init__(self):
-        if self.use_stateful_dataloader:
-            raise NotImplementedError("torchdata StatefulDataLoader is not supported by this build")
-
 
 @dataclass
 class ProjectConfiguration:

@@ -50,4 +50,11 @@ def _no(*args, **kwargs) -> bool:
 is_mps_available = is_hpu_available = is_xpu_available = is_npu_available = is_mlu_available = is_musa_available = _no
 is_sdaa_available = is_neuron_available = is_torch_xla_available = is_deepspeed_available = is_megatron_lm_available = _no
 is_fp8_available = is_torchao_available = is_transformer_engine_available = is_msamp_available = is_bnb_available = _no
-is_torchdata_stateful_dataloader_available = _no
+
+
+def is_torchdata_stateful_dataloader_available() -> bool:
+    """torchdata >= 0.8 ships ``torchdata.stateful_dataloader.StatefulDataLoader``."""
+    try:
+        return importlib.util.find_spec("torchdata.stateful_dataloader") is not None
+    except ModuleNotFoundError:
+        return False

@@ -151,7 +151,7 @@ def install():
                     "require_cpu": not cuda, "require_datasets": importlib.util.find_spec("datasets") is not None,
                     "require_non_torch_xla": True, "require_non_hpu": True, "require_fp16": True,
                     "require_non_cpu": cuda, "require_cuda": cuda, "require_cuda_or_xpu": cuda, "require_multi_device": False,
-                    "require_torchdata_stateful_dataloader": False,  # not supported by this build
+                    "require_torchdata_stateful_dataloader": importlib.util.find_spec("torchdata") is not None,
                 }.get(name, False)  # fmt: skip
                 if name == "require_torch_min_version":
                     return lambda version=None: (lambda test: test)
@@ -192,8 +192,7 @@ def install():
 
 def data_loop_on_cpu(path):
     """test_distributed_data_loop.py minus its join_uneven_inputs cases — those need one GPU per process (on MULTI_CPU the
-    reference's join is a documented no-op and uneven inputs would simply hang DDP) — and minus the torchdata
-    StatefulDataLoader cases; everything else runs as written."""
+    reference's join is a documented no-op and uneven inputs would simply hang DDP); everything else runs as written."""
     import torch
     from torch.utils.data import BatchSampler, DataLoader, RandomSampler, default_collate
 
@@ -212,7 +211,8 @@ def data_loop_on_cpu(path):
     sampler = BatchSampler(RandomSampler(dataset), batch_size=bs, drop_last=False)
     G["test_data_loader"](DataLoader(dataset, sampler=sampler, batch_size=None, collate_fn=default_collate, num_workers=workers),
                           accelerator)  # fmt: skip
-    # (test_stateful_dataloader*: torchdata's StatefulDataLoader is not supported by this build)
+    G["test_stateful_dataloader"](accelerator)
+    G["test_stateful_dataloader_save_state"](accelerator)
     accelerator.end_training()
 
 

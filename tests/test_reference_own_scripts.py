@@ -46,7 +46,7 @@ def test_reference_distributed_scripts():
 # ---- the reference's unit-test FILES (reference/tests/*.py) under pytest, same import alias --------------------------
 # Deselected, with the reason: environment artefacts of this container, or features outside the data-parallel scope.
 UNIT_FILES = {
-    "tests/test_data_loader.py": [],  # 19 run; the torchdata StatefulDataLoader cases skip (not supported)
+    "tests/test_data_loader.py": [],  # all 31, the torchdata StatefulDataLoader cases included
     "tests/test_optimizer.py": [],
     "tests/test_scheduler.py": [],
     "tests/test_state_checkpointing.py": [],
