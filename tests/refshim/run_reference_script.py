@@ -53,7 +53,7 @@ class StubModule(types.ModuleType):
 
 
 OUT_OF_SCOPE_MODULES = ("accelerate.big_modeling", "accelerate.hooks", "accelerate.utils.modeling", "accelerate.utils.memory",
-                        "accelerate.utils.offload", "accelerate.tracking", "accelerate.logging", "accelerate.inference")  # fmt: skip
+                        "accelerate.utils.offload", "accelerate.tracking", "accelerate.inference")  # fmt: skip
 OUT_OF_SCOPE_NAMES = {
     "accelerate_b200": ["infer_auto_device_map", "init_empty_weights", "load_checkpoint_and_dispatch", "cpu_offload",
                         "dispatch_model", "notebook_launcher", "find_executable_batch_size"],
