@@ -16,6 +16,7 @@ from .reducer import B200DataParallel
 from .scheduler import AcceleratedScheduler
 from .state import AcceleratorState, GradientState, PartialState
 from .utils import (
+    find_executable_batch_size,
     synchronize_rng_states,
     AutocastKwargs,
     DataLoaderConfiguration,

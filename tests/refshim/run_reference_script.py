@@ -52,7 +52,7 @@ class StubModule(types.ModuleType):
         return OutOfScope(f"{self.__name__}.{item}")
 
 
-OUT_OF_SCOPE_MODULES = ("accelerate.big_modeling", "accelerate.hooks", "accelerate.utils.modeling", "accelerate.utils.memory",
+OUT_OF_SCOPE_MODULES = ("accelerate.big_modeling", "accelerate.hooks", "accelerate.utils.modeling",
                         "accelerate.utils.offload", "accelerate.tracking", "accelerate.inference")  # fmt: skip
 OUT_OF_SCOPE_NAMES = {
     "accelerate_b200": ["infer_auto_device_map", "init_empty_weights", "load_checkpoint_and_dispatch", "cpu_offload",
@@ -167,6 +167,7 @@ def install():
     testing.DEFAULT_LAUNCH_COMMAND = ["torchrun", "--nproc_per_node=1"]
     testing.are_the_same_tensors = are_the_same_tensors
     testing.assert_exception = assert_exception
+    testing.memory_allocated_func = torch.cuda.memory_allocated if cuda else (lambda *a: 0)
     testing.path_in_accelerate_package = lambda *parts: os.path.join(REF, *parts)
     testing.get_launch_command = lambda **kw: ["torchrun"] + [f"--{k}={v}" for k, v in kw.items()]
 

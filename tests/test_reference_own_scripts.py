@@ -54,6 +54,7 @@ UNIT_FILES = {
     "tests/test_cpu.py": [],  # test_ops + test_script under debug_launcher
     "tests/test_kwargs_handlers.py": [],
     "tests/test_logging.py": [],
+    "tests/test_memory_utils.py": [],
     "tests/test_utils.py": [
         "::UtilsTester::test_patch_environment_key_exists",  # this image exports CC=/opt/gcc/bin/gcc; the test uses "CC"
         "::UtilsTester::test_convert_to_fp32",  # torch.compile / inductor cannot build in this container
@@ -75,7 +76,7 @@ def _run_unit_file(path):
 
 
 def test_reference_unit_test_files():
-    """Ten files of the reference's unit-test suite, run concurrently (each in its own interpreter)."""
+    """Eleven files of the reference's unit-test suite, run concurrently (each in its own interpreter)."""
     from concurrent.futures import ThreadPoolExecutor
 
     with ThreadPoolExecutor(max_workers=4) as pool:
