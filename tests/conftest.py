@@ -54,3 +54,28 @@ def run_distributed(script, nproc, *args, env=None, timeout=600):
     out = res.stdout + "\n" + res.stderr
     assert res.returncode == 0, f"{' '.join(cmd)} failed ({res.returncode}):\n{out[-6000:]}"
     return out
+
+
+def run_concurrently(jobs, max_workers=3):
+    """jobs: {label: thunk}.  Run them in a thread pool (each thunk launches its own subprocesses); a thunk that
+    raised is retried ONCE, alone — a loaded machine can time a rendezvous out — and only a second failure counts.
+    Returns {label: result}; raises AssertionError listing every label that failed twice."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    with ThreadPoolExecutor(max_workers=max_workers) as pool:
+        futures = {label: pool.submit(thunk) for label, thunk in jobs.items()}
+    results, failures = {}, {}
+    for label, fut in futures.items():
+        first = fut.exception()
+        if first is None:
+            results[label] = fut.result()
+            continue
+        import warnings
+
+        warnings.warn(f"{label} needed a retry after: {str(first)[-1500:]}")
+        try:
+            results[label] = jobs[label]()
+        except BaseException as second:  # noqa: BLE001 - reported below
+            failures[label] = f"first attempt: {first!r}\nretry: {second!r}"
+    assert not failures, "\n\n".join(f"{label}:\n{why}" for label, why in failures.items())
+    return results

@@ -7,7 +7,7 @@ import os
 
 import pytest
 
-from conftest import run_distributed
+from conftest import run_concurrently, run_distributed
 
 REF = "/root/reference/src"
 pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
@@ -77,12 +77,13 @@ def test_same_script_under_both_libraries(tmp_path):
     """The four differential checks above, run concurrently (each launches its own torchrun groups):
     training loop (7 variants, 2 ranks), collective / process-control / checkpoint API (3 ranks), prepared dataloaders
     (~70 configurations, 3 ranks), mid-epoch save/resume across the libraries (2 ranks)."""
-    from concurrent.futures import ThreadPoolExecutor
-
     checks = {"training_loop": check_training_loop, "api": check_api, "dataloaders": check_dataloaders, "resume": check_resume}
-    for name in checks:
-        (tmp_path / name).mkdir()
-    with ThreadPoolExecutor(max_workers=4) as pool:
-        futures = {name: pool.submit(fn, tmp_path / name) for name, fn in checks.items()}
-    errors = {name: f.exception() for name, f in futures.items() if f.exception() is not None}
-    assert not errors, "\n\n".join(f"{name}: {err!r}" for name, err in errors.items())
+    attempt = {name: 0 for name in checks}
+
+    def fresh_dir(name):  # a retry must not trip over the files of the first attempt
+        attempt[name] += 1
+        d = tmp_path / f"{name}_{attempt[name]}"
+        d.mkdir()
+        return d
+
+    run_concurrently({name: (lambda n=name, fn=fn: fn(fresh_dir(n))) for name, fn in checks.items()}, max_workers=4)

@@ -8,7 +8,7 @@ import sys
 
 import pytest
 
-from conftest import run_distributed
+from conftest import run_concurrently, run_distributed
 
 REF = "/root/reference/src/accelerate/test_utils/scripts"
 pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
@@ -33,14 +33,14 @@ def test_reference_distributed_scripts():
     broadcast / pad / reduce, debug-mode shape checks; 4 ranks), test_script.py (process control, RNG sync, dataloader
     preparation, training_check incl. bf16 and fp16-on-CPU, splits; 2 ranks and 1 process), test_distributed_data_loop.py
     (2 ranks) — run concurrently."""
-    from concurrent.futures import ThreadPoolExecutor
-
-    jobs = [(launch, "test_sync.py", 2), (launch, "test_ops.py", 4), (launch, "test_script.py", 2),
-            (launch, "test_distributed_data_loop.py", 2), (_single_process, "test_script.py")]  # fmt: skip
-    with ThreadPoolExecutor(max_workers=3) as pool:
-        futures = [(job[1:], pool.submit(job[0], *job[1:])) for job in jobs]
-    errors = [(what, f.exception()) for what, f in futures if f.exception() is not None]
-    assert not errors, "\n\n".join(f"{what}: {err!r}" for what, err in errors)
+    jobs = {
+        "test_sync.py x2": lambda: launch("test_sync.py", 2),
+        "test_ops.py x4": lambda: launch("test_ops.py", 4),
+        "test_script.py x2": lambda: launch("test_script.py", 2),
+        "test_distributed_data_loop.py x2": lambda: launch("test_distributed_data_loop.py", 2),
+        "test_script.py x1": lambda: _single_process("test_script.py"),
+    }
+    run_concurrently(jobs, max_workers=3)
 
 
 # ---- the reference's unit-test FILES (reference/tests/*.py) under pytest, same import alias --------------------------
@@ -77,10 +77,10 @@ def _run_unit_file(path):
 
 def test_reference_unit_test_files():
     """Eleven files of the reference's unit-test suite, run concurrently (each in its own interpreter)."""
-    from concurrent.futures import ThreadPoolExecutor
+    def checked(path):
+        _, ok, summary, tail = _run_unit_file(path)
+        assert ok, tail
+        return summary
 
-    with ThreadPoolExecutor(max_workers=4) as pool:
-        results = list(pool.map(_run_unit_file, sorted(UNIT_FILES)))
-    failed = [(path, tail) for path, ok, _, tail in results if not ok]
-    assert not failed, "\n\n".join(f"{path}:\n{tail}" for path, tail in failed)
-    print("\n".join(f"{path}: {summary}" for path, _, summary, _ in results))
+    results = run_concurrently({path: (lambda p=path: checked(p)) for path in sorted(UNIT_FILES)}, max_workers=4)
+    print("\n".join(f"{path}: {summary}" for path, summary in results.items()))
