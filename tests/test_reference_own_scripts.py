@@ -61,6 +61,8 @@ UNIT_FILES = {
     ],
     "tests/test_accelerator.py": [
         "::AcceleratorTester::test_prepare_model_8bit_cpu_offload_raises_valueerror_not_typeerror",  # bitsandbytes path
+        # compares psutil's SYSTEM-wide available RAM before/after: meaningless while other tests run concurrently
+        "::AcceleratorTester::test_free_memory_dereferences_prepared_components",
     ],
 }
 
