@@ -697,7 +697,7 @@ class Accelerator:
         gc.collect()
         if torch.cuda.is_available():
             torch.cuda.empty_cache()
-        return tuple(None for _ in objects) if len(objects) != 1 else None
+        return [None for _ in objects]  # `a, b = accelerator.free_memory(a, b)` (a list, as in the reference)
 
     clear = free_memory
 
