@@ -37,11 +37,12 @@ def test_user_comm_hook_on_cuda_single_process():
         torch.cuda.synchronize()
         assert [c[0] for c in calls] == list(range(len(ddp.reducer.buckets))) and calls[-1][1] and all(c[2] for c in calls)
         for p, q in zip(model.parameters(), ref.parameters()):
-            assert torch.equal(p.grad, q.grad * 3.0), step
+            assert torch.allclose(p.grad, q.grad * 3.0, rtol=1e-6, atol=1e-9), step
     # the fused statistics are not available behind a user hook: clipping takes the multi-tensor kernels
     assert ddp.reducer.stats_valid is False
     total = acc.clip_grad_norm_(ddp.parameters(), 0.1)
     want = torch.sqrt(sum((q.grad.double() * 3.0).pow(2).sum() for q in ref.parameters()))
     assert acc.last_clip_mode == "multi_tensor" and abs(total.item() - want.item()) <= 1e-5 * want.item()
-    PartialStateRuntime = acc.state.runtime
-    PartialStateRuntime.ctx.check_status()
+    from accelerate_b200.state import PartialState
+
+    PartialState().runtime.ctx.check_status()
