@@ -22,24 +22,38 @@ class TwoHeads(torch.nn.Module):
 
 
 def main():
-    os.environ["ACCELERATE_USE_CPU"] = "yes"
+    import argparse
+
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--device", default="cpu", choices=["cpu", "cuda"])
+    cuda = ap.parse_args().device == "cuda"
+    if not cuda:
+        os.environ["ACCELERATE_USE_CPU"] = "yes"
+    import torch.distributed as dist
     from torch.nn.parallel import DistributedDataParallel
 
     from accelerate_b200 import B200DataParallel
     from accelerate_b200.state import PartialState
 
-    state = PartialState(cpu=True)
+    state = PartialState(cpu=not cuda)
     rank = state.process_index
     torch.manual_seed(1 + rank)
     x = torch.randn(3, 4)
-    ours = B200DataParallel(TwoHeads(), find_unused_parameters=True)
-    ref = DistributedDataParallel(TwoHeads(), find_unused_parameters=True)
+    if cuda:  # ours on the GPU (used-map allreduce through b200dp_push); torch DDP on the CPU over its own gloo group
+        dev = state.device
+        ours = B200DataParallel(TwoHeads().to(dev), device_ids=[dev.index], find_unused_parameters=True)
+        ref = DistributedDataParallel(TwoHeads(), find_unused_parameters=True, process_group=dist.new_group(backend="gloo"))
+    else:
+        ours = B200DataParallel(TwoHeads(), find_unused_parameters=True)
+        ref = DistributedDataParallel(TwoHeads(), find_unused_parameters=True)
 
     def same(tag):
         for (n, p), q in zip(ours.module.named_parameters(), ref.module.parameters()):
             assert (p.grad is None) == (q.grad is None), (tag, n, p.grad is None, q.grad is None)
             if p.grad is not None:
-                assert torch.equal(p.grad, q.grad), (tag, n, (p.grad - q.grad).abs().max())
+                got = p.grad.cpu()
+                ok = torch.allclose(got, q.grad, rtol=1e-5, atol=1e-6) if cuda else torch.equal(got, q.grad)
+                assert ok, (tag, n, (got - q.grad).abs().max())
 
     for m in (ours, ref):  # A: nobody uses b
         m(x, False).sum().backward()
@@ -62,6 +76,8 @@ def main():
         m(x, False).sum().backward()
     assert float(ours.module.b.weight.grad.abs().sum()) == 0.0
     same("D")
+    if cuda:
+        state.runtime.ctx.check_status()
     print(f"UNUSED_OK rank {rank}", flush=True)
     state.destroy_process_group()
 
