@@ -178,6 +178,27 @@ def main():
         collected.extend(acc.gather_for_metrics(b, use_gather_object=True))
     log["gather_objects_for_metrics"] = ser(collected)
 
+    # model-facing helpers: value clipping, unwrap / state-dict names, sharded save_model layout, free_memory
+    torch.manual_seed(1)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 40), torch.nn.BatchNorm1d(40), torch.nn.Linear(40, 3))
+    net_opt = torch.optim.SGD(net.parameters(), lr=0.1)
+    net, net_opt = acc.prepare(net, net_opt)
+    acc.backward(net(torch.randn(5, 6, generator=g)).square().sum() * 100)
+    acc.clip_grad_value_(net.parameters(), 0.25)
+    log["clip_grad_value"] = ser([p.grad for p in net.parameters()])
+    log["wrapped_state_dict_keys"] = sorted(net.state_dict())
+    log["get_state_dict_keys"] = sorted(acc.get_state_dict(net))
+    log["get_state_dict_wrapped_keys"] = sorted(acc.get_state_dict(net, unwrap=False))
+    log["unwrap_type"] = type(acc.unwrap_model(net)).__name__
+    model_dir = os.path.join(args.project, "saved_model")
+    acc.save_model(net, model_dir, max_shard_size=400)
+    acc.wait_for_everyone()
+    log["save_model_files"] = sorted(os.listdir(model_dir))
+    with open(os.path.join(model_dir, "model.safetensors.index.json")) as f:
+        log["save_model_index"] = json.load(f)
+    log["free_memory"] = ser(acc.free_memory(net_opt))
+    log["after_free_memory"] = [len(acc._models), len(acc._optimizers), len(acc._dataloaders)]
+
     dl = acc.prepare(torch.utils.data.DataLoader(list(range(22)), batch_size=3))
     log["skip_first"] = ser([b for b in acc.skip_first_batches(dl, 2)])
     log["dl_len"], log["dl_total"] = len(dl), getattr(dl, "total_dataset_length", None)
