@@ -809,6 +809,10 @@ class B200DataParallel(torch.nn.Module, Joinable):
     def join_hook(self, **kwargs):
         return _B200JoinHook(self, divide_by_initial_world_size=kwargs.get("divide_by_initial_world_size", True))
 
+    def join(self, divide_by_initial_world_size: bool = True, enable: bool = True, throw_on_early_termination: bool = False):
+        """``with model.join():`` — torch DDP's shorthand for ``Join([model], ...)`` (distributed.py:1798-1870)."""
+        return Join([self], enable, throw_on_early_termination, divide_by_initial_world_size=divide_by_initial_world_size)
+
     @property
     def join_device(self):
         return self.reducer.device

@@ -50,7 +50,7 @@ def main():
         opt = torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.5)
         g = torch.Generator().manual_seed(50 + rank)
         snaps = []
-        with Join([model]):
+        with (model.join() if find_unused else Join([model])):  # both spellings of the context
             for it in range(3 + 2 * rank):
                 x, y = torch.randn(5, 6, generator=g), torch.randn(5, 2, generator=g)
                 if cuda and name == "ours":
