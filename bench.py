@@ -164,8 +164,19 @@ def cpu_leg(model_name, steps, warmup, budget_s=25.0, micro_batch=1):
             break
     mean = sum(times) / len(times)
     return {"value": micro_batch / mean, "unit": "samples/s", "cores": cores, "kind": "port",
+            "n_params": sum(p.numel() for p in model.parameters()),
             "sample": f"{len(times)} steps x {micro_batch} sequence(s) of {SEQ} tokens, {model_name}, torch CPU bf16 autocast "
                       f"fwd/bwd + oracle (C, pthreads) clip_grad_norm + AdamW; {mean * 1e3:.0f} ms/step"}  # fmt: skip
+
+
+def workload_config(model_name, n_params, per_gpu_batch, world):
+    """The `config` both arms report: BASELINE.json's headline workload at this GPU count."""
+    return {
+        "workload": f"{model_name} ({n_params} params) bf16-autocast train step: fwd + bwd + gradient bucket allreduce "
+                    "+ clip_grad_norm_(1.0) + AdamW + zero_grad",
+        "global_batch": per_gpu_batch * world, "per_gpu_batch": per_gpu_batch, "seq_len": SEQ, "parallelism": f"dp{world}",
+        "bucket_cap_mb": 25,
+    }  # fmt: skip
 
 
 def run_reference_arm(args):
@@ -173,13 +184,16 @@ def run_reference_arm(args):
     if rank != 0:
         return
     leg = cpu_leg(args.model, max(1, args.steps), max(0, min(args.warmup, 2)), budget_s=150.0)
+    n_params = leg.pop("n_params")
     line = {
         "impl": "reference", "metric": "samples_per_sec", "value": leg["value"], "unit": "samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 / leg["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"{args.model} bf16 train step on host CPU cores (oracle port of the DDP grad path)",
-                   "seq_len": SEQ, "per_step_batch": 1},
+        # the GPU arm's workload and configuration; every CPU step is a bounded sample of it (`cpu_baseline.sample`)
+        "config": dict(workload_config(args.model, n_params, args.batch, args.gpus),
+                       cpu_path="torch CPU bf16 autocast fwd/bwd + oracle (C, pthreads) clip_grad_norm + AdamW on the host cores",
+                       per_step_batch=1),
         "cpu_baseline": leg,
         "e2e": {"value": leg["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -320,6 +334,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_leg:
         try:
             cpu = cpu_leg(args.model, steps=4, warmup=1, budget_s=25.0)
+            cpu.pop("n_params", None)
         except Exception as err:  # the CPU leg must never take the GPU result down
             cpu = {"value": None, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {err}"}
 
@@ -329,13 +344,11 @@ def main():
             "metric": "samples_per_sec", "value": gb * steps / (total_ms / 1e3), "unit": "samples/s",
             "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": total_ms / steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {
-                "workload": f"{args.model} ({n_params} params) bf16-autocast train step: fwd + bwd + fused bucket allreduce "
-                            "+ clip_grad_norm_(1.0) + AdamW + zero_grad",
-                "global_batch": gb, "per_gpu_batch": B, "seq_len": SEQ, "parallelism": f"dp{world}", "bucket_cap_mb": 25,
-                "l2": "per-step working set (1.4 GB grads + weights + activations) exceeds the 126 MB L2; no flush needed",
-                "clip_mode": clip_mode, "final_loss": float(last_loss.detach()), "optimizer_step": optimizer_step,
-            },
+            "config": dict(
+                workload_config(args.model, n_params, B, world),
+                l2="per-step working set (1.4 GB grads + weights + activations) exceeds the 126 MB L2; no flush needed",
+                clip_mode=clip_mode, final_loss=float(last_loss.detach()), optimizer_step=optimizer_step,
+            ),
             "e2e": {"value": gb * steps / (e2e_ms / 1e3), "unit": "samples/s", "h2d_bytes_per_step": B * SEQ * 8,
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / steps},
             "gpu_launches": launches,
