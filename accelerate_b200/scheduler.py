@@ -8,40 +8,38 @@ from .state import AcceleratorState, GradientState
 
 
 class AcceleratedScheduler:
+    # everything that is not about WHEN to step (get_last_lr, get_lr, state_dict, load_state_dict, print_lr,
+    # last_epoch, base_lrs, ...) is the wrapped scheduler's own business: see __getattr__
+
     def __init__(self, scheduler, optimizers, step_with_optimizer: bool = True, split_batches: bool = False):
         self.scheduler = scheduler
         self.optimizers = list(optimizers) if isinstance(optimizers, (list, tuple)) else [optimizers]
-        self.split_batches = split_batches
-        self.step_with_optimizer = step_with_optimizer
+        self.step_with_optimizer, self.split_batches = step_with_optimizer, split_batches
         self.gradient_state = GradientState()
 
-    def step(self, *args, **kwargs):
-        if not self.step_with_optimizer:
-            self.scheduler.step(*args, **kwargs)
-            return
-        if not self.gradient_state.sync_gradients:
-            if self.gradient_state.adjust_scheduler:
+    def __getattr__(self, name):
+        if name in ("scheduler", "__setstate__", "__getstate__") or name.startswith("__"):
+            raise AttributeError(name)  # (unpickling probes these before __init__ ran)
+        return getattr(self.scheduler, name)
+
+    def _times_to_advance(self) -> int:
+        """0 = hold still this call."""
+        state = self.gradient_state
+        if not state.sync_gradients:
+            if state.adjust_scheduler:
                 self.scheduler._step_count += 1  # keep warm-up lengths honest under accumulation
-            return
+            return 0
         if any(opt.step_was_skipped for opt in self.optimizers):
-            return  # fp16 overflow: the optimizer did nothing, neither do we
-        repeats = 1 if self.split_batches else AcceleratorState().num_processes
-        total = getattr(self.scheduler, "total_steps", None)
-        for _ in range(repeats):
-            if total is None or self.scheduler._step_count <= total:  # OneCycle-style schedulers must not overrun
-                self.scheduler.step(*args, **kwargs)
+            return 0  # fp16 overflow: the optimizer did nothing, neither do we
+        # one global batch per step when batches are split; otherwise each process consumed its own batch
+        return 1 if self.split_batches else AcceleratorState().num_processes
 
-    def get_last_lr(self):
-        return self.scheduler.get_last_lr()
-
-    def state_dict(self):
-        return self.scheduler.state_dict()
-
-    def load_state_dict(self, state_dict):
-        self.scheduler.load_state_dict(state_dict)
-
-    def get_lr(self):
-        return self.scheduler.get_lr()
-
-    def print_lr(self, *args, **kwargs):
-        return self.scheduler.print_lr(*args, **kwargs)
+    def step(self, *args, **kwargs):
+        inner = self.scheduler
+        if not self.step_with_optimizer:
+            inner.step(*args, **kwargs)
+            return
+        budget = getattr(inner, "total_steps", None)  # OneCycle-style schedulers must not overrun their length
+        for _ in range(self._times_to_advance()):
+            if budget is None or inner._step_count <= budget:
+                inner.step(*args, **kwargs)
