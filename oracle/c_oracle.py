@@ -30,6 +30,9 @@ def load():
         lib.oracle_inv_scale.restype = ctypes.c_float
         lib.oracle_scale_f32.argtypes = [fp, ctypes.c_size_t, ctypes.c_float]
         lib.oracle_clamp_f32.argtypes = [fp, ctypes.c_size_t, ctypes.c_float]
+        d = ctypes.c_double
+        lib.oracle_adam_step_f32.argtypes = [fp, fp, fp, fp, ctypes.c_size_t, d, d, d, d, d, d, d, ctypes.c_float]
+        lib.oracle_adam_step_f32.restype = None
         _lib = lib
     return _lib
 
@@ -58,3 +61,16 @@ def clip_grad_norm_inplace(grads, max_norm):
     for g in grads:
         lib.oracle_scale_f32(_fp(g), g.size, coef)
     return tn
+
+
+def adam_step(p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, decoupled=True, mult=1.0):
+    """Same contract as ``ddp_oracle.adam_step`` (returns new p, m, v) with TRUE single-rounding fmas (C ``fmaf``),
+    i.e. the exact roundings of torch's CUDA foreach functors and of ``b200dp_multi_adam``."""
+    lib = load()
+    p, m, v = (np.ascontiguousarray(a, dtype=np.float32).reshape(-1).copy() for a in (p, m, v))
+    g = np.ascontiguousarray(g, dtype=np.float32).reshape(-1)
+    decay_mul = (1 - lr * weight_decay) if (decoupled and weight_decay != 0) else 1.0
+    l2 = weight_decay if (not decoupled and weight_decay != 0) else 0.0
+    lib.oracle_adam_step_f32(_fp(p), _fp(g), _fp(m), _fp(v), p.size, decay_mul, l2, beta1, beta2,
+                             -(lr / (1 - beta1**step)), (1 - beta2**step) ** 0.5, eps, np.float32(mult))  # fmt: skip
+    return p, m, v

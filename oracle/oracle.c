@@ -149,3 +149,36 @@ void oracle_clamp_f32(float* x, size_t n, float v) {
   scale_arg a = {x, v};
   parallel_for(n, clamp_body, &a);
 }
+
+/* One Adam / AdamW update in float32 with the roundings torch's CUDA foreach functors have (a + alpha*b inside one
+ * functor is a single fma; sqrt and division correctly rounded) — reference: optimizer.py:145-181 -> torch/optim/adam.py
+ * `_multi_tensor_adam`.  This file is built with -ffp-contract=off, so every fma below is explicit.
+ *   decay_mul = 1 - lr*wd (AdamW) or 1; l2 = wd (Adam) or 0; lerp_w = float(1-beta1); omb2 = float(1-beta2);
+ *   neg_step = -lr/(1-beta1^t); bc2_sqrt = sqrt(1-beta2^t); mult = clip coefficient x 1/loss-scale. */
+typedef struct {
+  float *p, *m, *v; const float* g;
+  float decay_mul, l2, lerp_w, beta2, omb2, neg_step, bc2_sqrt, eps, mult;
+} adam_arg;
+static void adam_body(size_t lo, size_t hi, void* ptr, int tid) {
+  (void)tid;
+  adam_arg* a = (adam_arg*)ptr;
+  for (size_t i = lo; i < hi; ++i) {
+    float p = a->p[i], m = a->m[i], v = a->v[i];
+    float g = a->g[i] * a->mult;
+    if (a->decay_mul != 1.0f) p = p * a->decay_mul;
+    if (a->l2 != 0.0f) g = fmaf(a->l2, p, g);
+    const float diff = g - m;
+    m = fabsf(a->lerp_w) < 0.5f ? fmaf(a->lerp_w, diff, m) : g - diff * (1.0f - a->lerp_w);
+    v = v * a->beta2;
+    v = fmaf(a->omb2, g * g, v);
+    const float denom = sqrtf(v) / a->bc2_sqrt + a->eps;
+    p = fmaf(a->neg_step, m / denom, p);
+    a->p[i] = p; a->m[i] = m; a->v[i] = v;
+  }
+}
+void oracle_adam_step_f32(float* p, const float* g, float* m, float* v, size_t n, double decay_mul, double l2,
+                          double beta1, double beta2, double neg_step, double bc2_sqrt, double eps, float mult) {
+  adam_arg a = {p, m, v, g, (float)decay_mul, (float)l2, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2),
+                (float)neg_step, (float)bc2_sqrt, (float)eps, mult};
+  parallel_for(n, adam_body, &a);
+}

@@ -386,4 +386,14 @@ def test_multi_adam_matches_oracle(rt, decoupled):
         np.testing.assert_allclose(p_dev[i].cpu().numpy(), want_p, rtol=2e-6, atol=1e-9, err_msg=f"param {i}")
         np.testing.assert_allclose(m_got[offs[i] : offs[i] + n], want_m, rtol=2e-6, atol=1e-10, err_msg=f"exp_avg {i}")
         np.testing.assert_allclose(v_got[offs[i] : offs[i] + n], want_v, rtol=2e-6, atol=1e-14, err_msg=f"exp_avg_sq {i}")
+    # ... and BIT-exact against the C oracle, whose fmaf / sqrtf / division round exactly like the kernel's intrinsics
+    from oracle import c_oracle
+
+    for i, n in enumerate(sizes[:8]):
+        want_p, want_m, want_v = c_oracle.adam_step(
+            host["p"][i].numpy(), host["g"][i].numpy(), host["m"][i].numpy(), host["v"][i].numpy(), step, lr, beta1, beta2,
+            eps, wd, decoupled=decoupled, mult=0.625,
+        )  # fmt: skip
+        assert np.array_equal(p_dev[i].cpu().numpy(), want_p), f"param {i} differs from the C oracle in some bits"
+        assert np.array_equal(m_got[offs[i] : offs[i] + n], want_m) and np.array_equal(v_got[offs[i] : offs[i] + n], want_v)
     rt.ctx.check_status()
