@@ -22,10 +22,15 @@ class Net(torch.nn.Module):
         self.bn = torch.nn.BatchNorm1d(16)
         self.head = torch.nn.Linear(16, 50, bias=False)
         self.head.weight = self.emb.weight  # tied, like GPT-2's wte / lm_head
+        self.frozen = torch.nn.Linear(16, 16)  # never trained: not the reducer's business
+        for p in self.frozen.parameters():
+            p.requires_grad_(False)
+        self.gain = torch.nn.Parameter(torch.ones(16, dtype=torch.bfloat16))  # a second gradient dtype (own buckets)
 
     def forward(self, ids):
         h = self.norm(self.emb(ids)).mean(dim=1)
-        h = self.bn(torch.tanh(self.fc(h)))
+        h = self.fc(torch.tanh(self.fc(h)))  # one module applied twice: its gradients accumulate inside one backward
+        h = self.bn(h + 0.1 * self.frozen(h)) * self.gain.float()
         return self.head(h)
 
 
