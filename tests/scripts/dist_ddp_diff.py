@@ -26,10 +26,16 @@ class Net(torch.nn.Module):
         for p in self.frozen.parameters():
             p.requires_grad_(False)
         self.gain = torch.nn.Parameter(torch.ones(16, dtype=torch.bfloat16))  # a second gradient dtype (own buckets)
+        self.side = torch.nn.Linear(16, 16)  # only used when `branch` says so (find_unused_parameters runs)
+        self.branch = 0
 
     def forward(self, ids):
         h = self.norm(self.emb(ids)).mean(dim=1)
         h = self.fc(torch.tanh(self.fc(h)))  # one module applied twice: its gradients accumulate inside one backward
+        if self.branch == 1:
+            h = h + self.side(h)
+        elif self.branch == 2:  # skips `fc` entirely on top of it
+            h = self.side(self.norm(self.emb(ids)).mean(dim=1))
         h = self.bn(h + 0.1 * self.frozen(h)) * self.gain.float()
         return self.head(h)
 
@@ -45,8 +51,14 @@ def main():
     state = PartialState(cpu=True)
     rank, world = state.process_index, state.num_processes
     assert world == 2
-    ours = B200DataParallel(Net(), bucket_cap_mb=0.0005)  # several buckets
-    ref = DistributedDataParallel(Net(), bucket_cap_mb=0.0005)
+    unused = os.environ.get("DDP_DIFF_UNUSED", "0") == "1"  # ranks take different branches: locally unused parameters
+    ours = B200DataParallel(Net(), bucket_cap_mb=0.0005, find_unused_parameters=unused)  # several buckets
+    ref = DistributedDataParallel(Net(), bucket_cap_mb=0.0005, find_unused_parameters=unused)
+
+    def pick_branch():
+        choice = plan.choice([1, 1, 2, (1, 2), (2, 1), (1, 1)]) if unused else 1
+        branch = choice[rank] if isinstance(choice, tuple) else choice
+        ours.module.branch = ref.module.branch = branch
     assert len(ours.reducer.buckets) > 1
     data = torch.Generator().manual_seed(100 + rank)  # per-rank data
     plan = random.Random(int(os.environ.get("DDP_DIFF_SEED", "7")))  # the same sequence of actions on both ranks
@@ -66,6 +78,7 @@ def main():
     syncs = 0
     for it in range(40):
         action = plan.choice(["sync", "sync", "accumulate", "eval", "double_forward", "zero_keep", "zero_none", "sgd"])
+        pick_branch()
         if action == "sync":
             x, y = batch()
             for m in (ours, ref):
