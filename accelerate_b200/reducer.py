@@ -348,8 +348,10 @@ class GradReducer:
             if self.user_hook is not None:
                 self._run_user_hook(b)
                 return
-            if self.wire_dtype is not None and b.flat.dtype == torch.float32:
-                # torch's compress hook: buffer.to(dtype).div_(N) -> allreduce -> copy back (default_hooks._compress_hook)
+            if self.wire_dtype is not None and b.flat.dtype != self.wire_dtype:
+                # torch's compress hook, for every bucket whatever its dtype: buffer.to(dtype).div_(N) -> allreduce ->
+                # copy back (default_hooks._compress_hook).  (The CUDA path compresses fp32 buckets only; half-precision
+                # parameters under the OTHER half-precision hook keep their own dtype on the wire there.)
                 narrow = b.flat.to(self.wire_dtype).div_(self.world)
                 if self.world > 1:
                     dist.all_reduce(narrow, op=dist.ReduceOp.SUM, group=self.process_group)

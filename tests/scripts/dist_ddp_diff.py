@@ -55,6 +55,15 @@ def main():
     ours = B200DataParallel(Net(), bucket_cap_mb=0.0005, find_unused_parameters=unused)  # several buckets
     ref = DistributedDataParallel(Net(), bucket_cap_mb=0.0005, find_unused_parameters=unused)
 
+    hook = os.environ.get("DDP_DIFF_HOOK", "")  # "fp16" / "bf16": torch's compress hooks vs the wire-format path
+    if hook:
+        from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
+
+        from accelerate_b200 import DDPCommunicationHookType
+
+        ours.register_comm_hook(None, DDPCommunicationHookType(hook))
+        ref.register_comm_hook(None, getattr(default_hooks, f"{hook}_compress_hook"))
+
     def pick_branch():
         choice = plan.choice([1, 1, 2, (1, 2), (2, 1), (1, 1)]) if unused else 1
         branch = choice[rank] if isinstance(choice, tuple) else choice

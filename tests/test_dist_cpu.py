@@ -42,13 +42,14 @@ def test_unused_parameters_match_torch_ddp():
     assert out.count("UNUSED_OK") == 2, out[-3000:]
 
 
-@pytest.mark.parametrize("seed,unused", [(7, "0"), (3, "0"), (11, "1")])
-def test_differential_against_torch_ddp(seed, unused):
+@pytest.mark.parametrize("seed,unused,hook", [(7, "0", ""), (3, "0", "bf16"), (11, "1", ""), (5, "0", "fp16")])
+def test_differential_against_torch_ddp(seed, unused, hook):
     """A random, rank-consistent sequence of sync / no_sync / zero_grad / eval / repeated-forward steps on a model with
     tied weights, frozen and bf16 parameters, a module applied twice and BatchNorm buffers — with ``unused`` the ranks
-    also take different branches under find_unused_parameters=True: gradients (including which are None) AND buffers
+    also take different branches under find_unused_parameters=True, with ``hook`` both sides compress (torch's
+    fp16/bf16_compress_hook vs the wire-format path): gradients (including which are None) AND buffers
     bit-equal to torch DistributedDataParallel (gloo, N=2)."""
-    out = run_distributed("dist_ddp_diff.py", 2, timeout=300, env={"DDP_DIFF_SEED": str(seed), "DDP_DIFF_UNUSED": unused})
+    out = run_distributed("dist_ddp_diff.py", 2, timeout=300, env={"DDP_DIFF_SEED": str(seed), "DDP_DIFF_UNUSED": unused, "DDP_DIFF_HOOK": hook})
     assert out.count("DDP_DIFF_OK") == 2, out[-3000:]
 
 
