@@ -52,8 +52,9 @@ def main():
     rank, world = state.process_index, state.num_processes
     assert world == 2
     unused = os.environ.get("DDP_DIFF_UNUSED", "0") == "1"  # ranks take different branches: locally unused parameters
-    ours = B200DataParallel(Net(), bucket_cap_mb=0.0005, find_unused_parameters=unused)  # several buckets
-    ref = DistributedDataParallel(Net(), bucket_cap_mb=0.0005, find_unused_parameters=unused)
+    bcast = os.environ.get("DDP_DIFF_NO_BCAST", "0") != "1"  # broadcast_buffers=False: BatchNorm statistics stay per rank
+    ours = B200DataParallel(Net(), bucket_cap_mb=0.0005, find_unused_parameters=unused, broadcast_buffers=bcast)  # several buckets
+    ref = DistributedDataParallel(Net(), bucket_cap_mb=0.0005, find_unused_parameters=unused, broadcast_buffers=bcast)
 
     hook = os.environ.get("DDP_DIFF_HOOK", "")  # "fp16" / "bf16": torch's compress hooks vs the wire-format path
     if hook:

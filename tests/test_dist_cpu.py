@@ -49,7 +49,8 @@ def test_differential_against_torch_ddp(seed, unused, hook):
     also take different branches under find_unused_parameters=True, with ``hook`` both sides compress (torch's
     fp16/bf16_compress_hook vs the wire-format path): gradients (including which are None) AND buffers
     bit-equal to torch DistributedDataParallel (gloo, N=2)."""
-    out = run_distributed("dist_ddp_diff.py", 2, timeout=300, env={"DDP_DIFF_SEED": str(seed), "DDP_DIFF_UNUSED": unused, "DDP_DIFF_HOOK": hook})
+    out = run_distributed("dist_ddp_diff.py", 2, timeout=300, env={"DDP_DIFF_SEED": str(seed), "DDP_DIFF_UNUSED": unused, "DDP_DIFF_HOOK": hook,
+                               "DDP_DIFF_NO_BCAST": "1" if seed == 3 else "0"})  # fmt: skip
     assert out.count("DDP_DIFF_OK") == 2, out[-3000:]
 
 
