@@ -63,6 +63,13 @@ def main():
         log[f"pad_{sorted(kw.items())}"] = ser(acc.pad_across_processes(ragged, **kw))
     log["pad_nested"] = ser(acc.pad_across_processes({"r": ragged, "same": torch.ones(2, 2)}, dim=0))
     log["pad_int"] = ser(acc.pad_across_processes(torch.arange(3 + 2 * rank), pad_index=-1))
+    # degenerate shapes
+    log["gather_empty"] = ser(acc.gather(torch.empty(0, 3)))
+    log["gather_zero_dim_inside"] = ser(acc.gather(torch.zeros(2, 0, 4)))
+    log["reduce_empty"] = ser(acc.reduce(torch.empty(0), "sum"))
+    log["pad_from_empty"] = ser(acc.pad_across_processes(torch.ones(rank, 2), dim=0, pad_index=9))  # rank 0 holds nothing
+    log["pad_bool"] = ser(acc.pad_across_processes(torch.ones(1 + rank, dtype=torch.bool)))
+    log["pad_float_index_on_int"] = ser(acc.pad_across_processes(torch.arange(2 + rank), pad_index=0.5))
     payload = {"rank": rank, "words": ["x"] * (rank + 1), "t": [1.5, None]}
     log["gather_object"] = ser(utils.gather_object([payload, rank]))
     objs = [payload if rank == 0 else None, "keep" if rank == 0 else "drop"]
