@@ -26,7 +26,9 @@ from types import MethodType
 
 import torch
 
+from . import lazy_grad
 from .data_loader import prepare_data_loader, skip_first_batches
+from .lazy_grad import raw_grad
 from .optimizer import AcceleratedOptimizer
 from .reducer import B200DataParallel, live_reducers
 from .scheduler import AcceleratedScheduler
@@ -506,15 +508,17 @@ class Accelerator:
 
     def _fused_reducer_for(self, params):
         for red in live_reducers():
-            if red.is_cuda and red.stats_valid and red.manages(params):
+            red.finish_open_backward()
+            if red.is_cuda and red.stats_fresh() and red.manages(params):
                 return red
         return None
 
     def clip_grad_norm_(self, parameters, max_norm, norm_type=2):
         """Clip by global norm; returns the total norm (0-dim tensor).  On CUDA, when ``parameters`` are
         exactly a prepared model's parameters and this follows a sync backward, the norm comes from the
-        statistics the allreduce kernels produced and the only pass over the gradients is the multiply
-        (skipped entirely when the coefficient is 1)."""
+        statistics the allreduce kernels produced; the multiply by the coefficient stays *pending*
+        (``lazy_grad.py``): the fused Adam step applies it on the fly, anything else that looks at a gradient
+        first triggers the pass, so observable values are the reference's (accelerator.py:2946-3007)."""
         params = [parameters] if isinstance(parameters, torch.Tensor) else list(parameters)
         norm_type = float(norm_type)
         if self.device.type != "cuda":
@@ -522,38 +526,22 @@ class Accelerator:
             self.last_clip_mode = "torch"
             return torch.nn.utils.clip_grad_norm_(params, max_norm, norm_type=norm_type)
         red = self._fused_reducer_for(params) if norm_type in (2.0, math.inf) else None
+        defer = lazy_grad.enabled()
         if red is not None:
             scale = self.scaler._scale if (self.scaler is not None and self._scaler_pending(red)) else None
             if scale is not None and not red.unscaled:
                 # unscale and clip in ONE pass; tell the scaler its work is done
-                out = red.fused_clip_(float(max_norm), norm_type, scale=scale)
+                out = red.fused_clip_(float(max_norm), norm_type, scale=scale, defer=defer)
                 self._mark_unscaled(red, out)
             else:
                 self.unscale_gradients()
                 out = red.fused_clip_(float(max_norm), norm_type, scale=self.scaler._scale if red.unscaled else None,
-                                      defer=self._can_defer_clip(red))
+                                      defer=defer)
             self.last_clip_mode = "fused"
             return out[0]
         self.unscale_gradients()
         self.last_clip_mode = "multi_tensor"
-        return self._multi_tensor_clip(params, float(max_norm), norm_type)
-
-    def _can_defer_clip(self, red) -> bool:
-        """B200DP_DEFER_CLIP=1 and every optimizer owning these gradients will run the fused Adam step."""
-        if os.environ.get("B200DP_DEFER_CLIP", "0") != "1" or self.scaler is not None:
-            return False
-        owners = [o for o in self._optimizers if {id(p) for g in o.param_groups for p in g["params"]} & red._managed_ids]
-        if len(owners) != 1:  # the pending multiplier is handed over exactly once
-            return False
-        for o in owners:
-            if not o._fused_plan_tried:
-                o._fused_plan_tried = True
-                from .optimizer import FusedAdamPlan
-
-                o._fused_plan = FusedAdamPlan.try_build(o.optimizer)
-            if o._fused_plan is None or o._fused_plan.reducer is not red:
-                return False
-        return True
+        return self._multi_tensor_clip(params, float(max_norm), norm_type, defer=defer)
 
     def _scaler_pending(self, red) -> bool:
         """True when every optimizer holding this reducer's parameters still has scaled gradients."""
@@ -563,7 +551,7 @@ class Accelerator:
         if not owners:
             return False
         return all(self.scaler._per_optimizer_states[id(o)]["stage"] == OptState.READY for o in owners) and all(
-            {id(p) for g in o.param_groups for p in g["params"] if p.grad is not None} <= red._managed_ids for o in owners
+            {id(p) for g in o.param_groups for p in g["params"] if raw_grad(p) is not None} <= red._managed_ids for o in owners
         )
 
     def _owning_optimizers(self, red):
@@ -585,7 +573,7 @@ class Accelerator:
             st["found_inf_per_device"] = {self.device: out[2].clone()}
             st["stage"] = OptState.UNSCALED
 
-    def _multi_tensor_clip(self, params, max_norm: float, norm_type: float):
+    def _multi_tensor_clip(self, params, max_norm: float, norm_type: float, defer: bool = False):
         """Gradients outside a fusion buffer (world size 1, parameter subsets): two multi-tensor launches
         per dtype — statistics, then scale — instead of torch's foreach_norm/stack/norm/foreach_mul."""
         if norm_type not in (2.0, math.inf):
@@ -594,9 +582,10 @@ class Accelerator:
 
         rt = SymmRuntime.get()
         st = torch.cuda.current_stream(self.device).cuda_stream
+        lazy_grad.flush_all()  # an earlier pending multiplier belongs to these values
         by_dtype = {}
         for p in params:
-            g = p.grad
+            g = raw_grad(p)
             if g is None:
                 continue
             if g.device != self.device or not g.is_contiguous() or native_dtype(g.dtype) not in (0, 1, 2):
@@ -614,8 +603,17 @@ class Accelerator:
             if slot - rt._mt_slot_base > 64:
                 raise RuntimeError("too many gradient tensors for the multi-tensor clip")
         rt.ctx.finalize_norm(rt._mt_slot_base, slot - rt._mt_slot_base, False, norm_type, max_norm, None, out.data_ptr(), st)
-        for dtype, grads in by_dtype.items():
-            rt.ctx.multi_scale([g.data_ptr() for g in grads], [g.numel() for g in grads], native_dtype(dtype), out.data_ptr() + 4, st)
+
+        def apply():  # holds the gradient tensors alive until the multiplier is applied or consumed
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            for dtype, grads in by_dtype.items():
+                rt.ctx.multi_scale([g.data_ptr() for g in grads], [g.numel() for g in grads], native_dtype(dtype),
+                                   out.data_ptr() + 4, stream)  # fmt: skip
+
+        if defer:
+            lazy_grad.defer(out, apply, owner=frozenset(g.data_ptr() for grads in by_dtype.values() for g in grads))
+        else:
+            apply()
         return out[0]
 
     def clip_grad_value_(self, parameters, clip_value):
@@ -688,7 +686,7 @@ class Accelerator:
 
     def free_memory(self, *objects):
         for m in self._wrappers:
-            m.reducer.remove_hooks()
+            m.reducer.close()  # hooks, symmetric fusion/wire segments, statistics slots
         self._wrappers = []
         self._schedulers, self._optimizers, self._models, self._dataloaders = [], [], [], []
         self.step = 0

@@ -1,8 +1,9 @@
 """save_state / load_state for the prepared objects, file-compatible with the reference's checkpoints
 (``src/accelerate/checkpointing.py:63-338``, file names from ``utils/constants.py:20-36``):
 
-    model.safetensors | pytorch_model.bin   (``_1``, ``_2`` ... for further models; keys keep the wrapper's
-                                             ``module.`` prefix exactly like a DDP-wrapped model's do)
+    model.safetensors | pytorch_model.bin   (``_1``, ``_2`` ... for further models; keys are the UNWRAPPED module's,
+                                             no ``module.`` prefix: like the reference, ``Accelerator._models`` keeps
+                                             the module it was handed, not the data-parallel wrapper)
     optimizer.bin, scheduler.bin, sampler.bin, scaler.pt
     random_states_{process_index}.pkl       {"step", "random_state", "numpy_random_seed", "torch_manual_seed",
                                              "torch_cuda_manual_seed"}

@@ -1018,8 +1018,30 @@ static void pack_push(PackTable* t, int* n, uint32_t* acc, const char* s, char* 
   t->dst[*n] = d;
   t->bytes[*n] = bytes;
   t->chunk_start[*n] = *acc;
-  *acc += uint32_t((bytes + kPackChunk - 1) / kPackChunk);
+  *acc += uint32_t((bytes + t->chunk_bytes - 1) / t->chunk_bytes);
   ++*n;
+}
+
+struct BulkCfg {
+  int warps, stages, stage_bytes, ctas_per_sm;
+};
+static BulkCfg bulk_cfg() {
+  static const BulkCfg cfg = [] {
+    auto geti = [](const char* name, int dflt, int lo, int hi) {
+      const char* e = getenv(name);
+      int v = e ? atoi(e) : dflt;
+      return v < lo ? lo : (v > hi ? hi : v);
+    };
+    BulkCfg c;
+    c.warps = geti("B200DP_BULK_WARPS", 4, 1, kBulkMaxWarps);
+    c.stages = geti("B200DP_BULK_STAGES", 3, 2, kBulkMaxStages);
+    c.stage_bytes = geti("B200DP_BULK_STAGE_KB", 16, 1, 64) * 1024;
+    c.ctas_per_sm = geti("B200DP_BULK_CTAS_PER_SM", 1, 1, 4);
+    while (size_t(c.warps) * c.stages * c.stage_bytes > size_t(220) * 1024 / c.ctas_per_sm && c.stages > 2) --c.stages;
+    while (size_t(c.warps) * c.stages * c.stage_bytes > size_t(220) * 1024 / c.ctas_per_sm && c.warps > 1) --c.warps;
+    return c;
+  }();
+  return cfg;
 }
 
 extern "C" int b200dp_pack(b200dp_ctx* c, const void* const* srcs, void* const* dsts, const size_t* nbytes, int n,
@@ -1028,18 +1050,24 @@ extern "C" int b200dp_pack(b200dp_ctx* c, const void* const* srcs, void* const* 
   DeviceGuard g(c->device);
   cudaStream_t st = (cudaStream_t)stream;
   static thread_local PackTable bulk, plain;
+  const BulkCfg cfg = bulk_cfg();
+  bulk.chunk_bytes = uint32_t(cfg.stage_bytes);
+  plain.chunk_bytes = kPackChunk;
   int nb = 0, np = 0;
   uint32_t accb = 0, accp = 0;
   auto flush = [&](bool force) -> int {
     if (nb > 0 && (force || nb >= kMTMax - 1)) {
       bulk.chunk_start[nb] = accb;
       bulk.n = nb;
+      const size_t smem = size_t(cfg.warps) * cfg.stages * cfg.stage_bytes;
       if (!c->bulk_attr_set) {
-        RT(cudaFuncSetAttribute(pack_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBulkStages * kPackChunk));
+        RT(cudaFuncSetAttribute(pack_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         c->bulk_attr_set = true;
       }
-      int grid = int(accb) < c->sm_count ? int(accb) : c->sm_count;
-      pack_bulk_kernel<<<grid, 32, kBulkStages * kPackChunk, st>>>(bulk, c->d_status);
+      int want = int((accb + cfg.warps - 1) / cfg.warps);
+      int cap = c->sm_count * cfg.ctas_per_sm;
+      int grid = want < cap ? want : cap;
+      pack_bulk_kernel<<<grid, cfg.warps * 32, smem, st>>>(bulk, c->d_status, cfg.stages);
       KERNEL_OK(c);
       nb = 0;
       accb = 0;

@@ -19,8 +19,7 @@ constexpr int kThreads = 512;        // comm kernels: 1 CTA / SM, 16 warps of 16
 constexpr int kStreamThreads = 256;  // local HBM streaming kernels
 constexpr int kMTMax = 640;          // tensors per multi-tensor launch (table lives in kernel params)
 constexpr int kMTChunk = 8192;       // elements per chunk in multi_stats / multi_scale
-constexpr int kPackChunk = 32768;    // bytes per chunk in pack kernels (= one TMA bulk stage)
-constexpr int kBulkStages = 4;
+constexpr int kPackChunk = 32768;    // bytes per chunk in the LDG/STG pack kernel
 
 // ------------------------------------------------------------------------------------------------
 // statistics hand-off: every CTA leaves its partial, the last CTA to arrive folds them in a fixed
@@ -505,7 +504,8 @@ struct PackTable {
   const char* src[kMTMax];
   char* dst[kMTMax];
   unsigned long long bytes[kMTMax];
-  uint32_t chunk_start[kMTMax + 1];  // prefix sum of ceil(bytes / kPackChunk)
+  uint32_t chunk_start[kMTMax + 1];  // prefix sum of ceil(bytes / chunk_bytes)
+  uint32_t chunk_bytes;              // work unit: kPackChunk (LDG/STG) or one TMA stage (bulk)
   int n;
 };
 
@@ -518,19 +518,36 @@ __device__ __forceinline__ int find_tensor(const uint32_t* chunk_start, int n, u
   return lo;
 }
 
+// LDG/STG variant: any alignment.  A CTA takes 32 KB chunks; every thread keeps kPackILP 16-byte loads in flight
+// before the first store of a trip (256 threads x 4 x 16 B = 16 KB per CTA, x up to 8 CTAs per SM), which is what
+// covers HBM latency; no shared memory and few registers, so it co-resides with the backward GEMMs it overlaps.
+constexpr int kPackILP = 4;
 __global__ void __launch_bounds__(kStreamThreads) pack_kernel(const __grid_constant__ PackTable t) {
   const uint32_t total = t.chunk_start[t.n];
+  const size_t chunk_bytes = t.chunk_bytes;
   for (uint32_t c = blockIdx.x; c < total; c += gridDim.x) {
     const int ti = find_tensor(t.chunk_start, t.n, c);
-    const size_t off = size_t(c - t.chunk_start[ti]) * kPackChunk;
+    const size_t off = size_t(c - t.chunk_start[ti]) * chunk_bytes;
     const size_t rem = t.bytes[ti] - off;
-    const size_t n = rem < size_t(kPackChunk) ? rem : size_t(kPackChunk);
+    const size_t n = rem < chunk_bytes ? rem : chunk_bytes;
     const char* s = t.src[ti] + off;
     char* d = t.dst[ti] + off;
     const uintptr_t al = reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d);
     if ((al & 15) == 0) {
       const size_t nvec = n >> 4;
-      for (size_t i = threadIdx.x; i < nvec; i += blockDim.x) st_stream16(d + i * 16, ld_stream16(s + i * 16));
+      for (size_t i = threadIdx.x; i < nvec; i += size_t(kPackILP) * blockDim.x) {
+        uint4 v[kPackILP];
+#pragma unroll
+        for (int u = 0; u < kPackILP; ++u) {
+          const size_t j = i + size_t(u) * blockDim.x;
+          if (j < nvec) v[u] = ld_stream16(s + j * 16);
+        }
+#pragma unroll
+        for (int u = 0; u < kPackILP; ++u) {
+          const size_t j = i + size_t(u) * blockDim.x;
+          if (j < nvec) st_stream16(d + j * 16, v[u]);
+        }
+      }
       for (size_t i = (nvec << 4) + threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];
     } else if ((al & 3) == 0) {
       const size_t nw = n >> 2;
@@ -543,8 +560,9 @@ __global__ void __launch_bounds__(kStreamThreads) pack_kernel(const __grid_const
   }
 }
 
-// --- TMA-engine variant: one elected thread per CTA drives cp.async.bulk global->smem->global
-// through a ring of kBulkStages x 32 KB stages; the SM's LSU is idle, the copy engine streams.
+// --- TMA-engine variant: cp.async.bulk global->smem->global.  Every warp of the CTA elects one thread that drives its
+// own ring of `stages` stages (stage size = t.chunk_bytes) over the chunks g, g+G, ... (g = global warp index), so a
+// CTA has warps x stages bulk transfers in flight; the LSU and the register file stay idle, the copy engine streams.
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -581,40 +599,49 @@ __device__ __forceinline__ void bulk_wait_read() {
 }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+constexpr int kBulkMaxWarps = 8;
+constexpr int kBulkMaxStages = 8;
+
 // All spans must be 16-byte aligned with a size that is a multiple of 16 (the host splits off the rest).
-__global__ void __launch_bounds__(32) pack_bulk_kernel(const __grid_constant__ PackTable t, int* status) {
+__global__ void __launch_bounds__(kBulkMaxWarps * 32) pack_bulk_kernel(const __grid_constant__ PackTable t, int* status,
+                                                                        int stages) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) uint64_t full[kBulkStages];
-  if (threadIdx.x != 0) return;  // one elected thread; the TMA engine does the work
+  __shared__ __align__(8) uint64_t full_all[kBulkMaxWarps][kBulkMaxStages];
+  if ((threadIdx.x & 31) != 0) return;  // one elected thread per warp; the TMA engine does the work
+  const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  uint64_t* full = full_all[warp];
+  const uint32_t stage_bytes = t.chunk_bytes;
+  unsigned char* ring = smem + size_t(warp) * stages * stage_bytes;
   const uint32_t total = t.chunk_start[t.n];
-  for (int s = 0; s < kBulkStages; ++s) mbar_init(&full[s], 1);
+  for (int s = 0; s < stages; ++s) mbar_init(&full[s], 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 
+  const uint32_t g = blockIdx.x * nwarps + warp, G = gridDim.x * nwarps;
   auto chunk_of = [&](uint32_t j, const char*& s, char*& d, uint32_t& n) {
-    const uint32_t c = blockIdx.x + j * gridDim.x;
+    const uint32_t c = g + j * G;
     const int ti = find_tensor(t.chunk_start, t.n, c);
-    const size_t off = size_t(c - t.chunk_start[ti]) * kPackChunk;
+    const size_t off = size_t(c - t.chunk_start[ti]) * stage_bytes;
     const size_t rem = t.bytes[ti] - off;
-    n = uint32_t(rem < size_t(kPackChunk) ? rem : size_t(kPackChunk));
+    n = uint32_t(rem < size_t(stage_bytes) ? rem : size_t(stage_bytes));
     s = t.src[ti] + off;
     d = t.dst[ti] + off;
   };
-  const uint32_t mine = blockIdx.x < total ? (total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const uint32_t mine = g < total ? (total - g + G - 1) / G : 0;
   auto issue_load = [&](uint32_t j) {
     const char* s;
     char* d;
     uint32_t n;
     chunk_of(j, s, d, n);
-    const int st = j % kBulkStages;
+    const int st = j % stages;
     mbar_expect_tx(&full[st], n);
-    bulk_g2s(smem + size_t(st) * kPackChunk, s, n, &full[st]);
+    bulk_g2s(ring + size_t(st) * stage_bytes, s, n, &full[st]);
   };
-  const uint32_t pro = mine < uint32_t(kBulkStages) ? mine : uint32_t(kBulkStages);
+  const uint32_t pro = mine < uint32_t(stages) ? mine : uint32_t(stages);
   for (uint32_t j = 0; j < pro; ++j) issue_load(j);
   for (uint32_t j = 0; j < mine; ++j) {
-    const int st = j % kBulkStages;
-    const uint32_t parity = (j / kBulkStages) & 1;
+    const int st = j % stages;
+    const uint32_t parity = (j / stages) & 1;
     uint32_t spins = 0;
     while (!mbar_try_wait(&full[st], parity)) {
       if (++spins > (1u << 26)) {  // ~seconds: never hang the GPU on a lost transaction
@@ -626,12 +653,12 @@ __global__ void __launch_bounds__(32) pack_bulk_kernel(const __grid_constant__ P
     char* d;
     uint32_t n;
     chunk_of(j, s, d, n);
-    bulk_s2g(d, smem + size_t(st) * kPackChunk, n);
+    bulk_s2g(d, ring + size_t(st) * stage_bytes, n);
     bulk_commit();
     // refill the stage used by chunk j-1 once its store has finished reading shared memory
-    if (j >= 1 && (j - 1) + kBulkStages < mine) {
+    if (j >= 1 && (j - 1) + stages < mine) {
       bulk_wait_read<1>();
-      issue_load(j - 1 + kBulkStages);
+      issue_load(j - 1 + stages);
     }
   }
   bulk_wait_all();

@@ -39,8 +39,10 @@ _LOADER_KWARGS = {
     "batch_size": 1, "shuffle": False, "sampler": None, "batch_sampler": None, "num_workers": 0,
     "collate_fn": None, "pin_memory": False, "drop_last": False, "timeout": 0, "worker_init_fn": None,
     "multiprocessing_context": None, "generator": None, "prefetch_factor": None, "persistent_workers": False,
-    "pin_memory_device": "", "in_order": True,
+    "pin_memory_device": "",
 }  # fmt: skip
+if "in_order" in __import__("inspect").signature(DataLoader.__init__).parameters:  # torch >= 2.6 (the reference gates on the version)
+    _LOADER_KWARGS["in_order"] = True
 
 
 class SeedableRandomSampler(RandomSampler):

@@ -47,6 +47,10 @@ class LocalSGD:
         model = self.model
         if isinstance(model, B200DataParallel) and model.reducer.is_cuda and model.reducer.can_average_in_buffer():
             model.reducer.average_parameters_()
+            # the reference averages EVERY parameter (local_sgd.py:99-107); frozen ones have no slot in the fusion buffer
+            for param in model.parameters():
+                if not param.requires_grad:
+                    param.data = self.accelerator.reduce(param.data, reduction="mean")
             return
         with self.accelerator.autocast():
             for param in model.parameters():

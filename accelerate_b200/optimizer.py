@@ -14,6 +14,8 @@ import os
 
 import torch
 
+from . import lazy_grad
+from .lazy_grad import raw_grad
 from .state import AcceleratorState, GradientState
 
 
@@ -147,14 +149,17 @@ class FusedAdamPlan:
         """Gradient pointers for a loose-layout step, or None when this step is not eligible."""
         out = []
         for p in params:
-            g = p.grad
+            g = raw_grad(p)
             if g is None or g.dtype != torch.float32 or g.device != p.device or g.is_sparse or not g.is_contiguous():
                 return None
             out.append(g.data_ptr())
         return out
 
-    def step(self) -> bool:
-        """Run the fused update; False = not applicable right now (caller falls back to optimizer.step())."""
+    def step(self, found_inf: torch.Tensor | None = None) -> bool:
+        """Run the fused update; False = not applicable right now (caller falls back to optimizer.step()).
+
+        ``found_inf`` (GradScaler runs): 1-element float32 device tensor; the kernels return at once when it is
+        non-zero, so an overflowed step is skipped without the host ever reading the flag."""
         red = self.reducer
         pending = None
         if red is not None:
@@ -168,14 +173,22 @@ class FusedAdamPlan:
         self._adopt_state()  # cheap identity checks; heals optimizer.load_state_dict()
         stream = torch.cuda.current_stream(self.device).cuda_stream
         if red is not None:
-            pending = red.take_pending_multiplier()
+            pending = red.take_pending_multiplier()  # deferred clip / unscale: applied on the fly by the kernel
+        elif lazy_grad.has_pending():
+            pending = lazy_grad.take_for(frozenset(ptr for grads in grads_per_group for ptr in grads))
+            pending = pending.out if pending is not None else None
+        if lazy_grad.has_pending():
+            lazy_grad.flush_all()  # multipliers of other gradient sets: not ours to fold in
         mult_ptr = pending.data_ptr() + 4 if pending is not None else None
-        found_ptr = None  # without a GradScaler torch applies the update even to non-finite gradients: keep that
+        # without a GradScaler torch applies the update even to non-finite gradients: keep that (found_ptr None)
+        found_ptr = found_inf.data_ptr() if found_inf is not None else None
+        self.last_steps = []
         for pg, (params, table), grads in zip(self.optimizer.param_groups, self.tables, grads_per_group):
             if not params:
                 continue
             steps = [self.optimizer.state[p]["step"] for p in params]
             torch._foreach_add_(steps, 1)
+            self.last_steps.extend(steps)
             t = float(steps[0])
             lr, (beta1, beta2), eps, wd = float(pg["lr"]), pg["betas"], float(pg["eps"]), float(pg["weight_decay"])
             decoupled = pg.get("decoupled_weight_decay", self.decoupled_default)
@@ -185,8 +198,7 @@ class FusedAdamPlan:
             bc2_sqrt = (1 - beta2**t) ** 0.5
             self.ctx.multi_adam(table, self.m_flat.data_ptr(), self.v_flat.data_ptr(), decay_mul, l2, beta1, beta2,
                                 -(lr / bc1), bc2_sqrt, eps, mult_ptr, found_ptr, stream, grads=grads)  # fmt: skip
-        if pending is not None:
-            self._keepalive = pending  # the kernels read it asynchronously
+        self._keepalive = (pending, found_inf)  # the kernels read them asynchronously
         return True
 
 
@@ -201,6 +213,8 @@ class AcceleratedOptimizer(torch.optim.Optimizer):
         self._stepped = False  # set by the instrumented inner step
         self._fused_plan = None  # built lazily at the first step (parameters must be wrapped by then)
         self._fused_plan_tried = False
+        self._skip_pending = None  # (event, step counters) of a fused step under a GradScaler, not yet settled
+        self._skip_host = None
         if scaler is not None:
             self._arm_step_probe()
         if device_placement:
@@ -249,6 +263,7 @@ class AcceleratedOptimizer(torch.optim.Optimizer):
         self.optimizer.load_state_dict(state_dict)
 
     def state_dict(self):
+        self._settle_skip()  # `step` counters must be final
         return self.optimizer.state_dict()
 
     def train(self):
@@ -278,6 +293,9 @@ class AcceleratedOptimizer(torch.optim.Optimizer):
                 return
             self.optimizer.step(closure)
             return
+        self._settle_skip()
+        if closure is None and self._fused_scaled_step():
+            return
         self._stepped = False
         self.optimizer.step = self._probed_step
         try:
@@ -287,7 +305,7 @@ class AcceleratedOptimizer(torch.optim.Optimizer):
             self.optimizer.step = self._inner_step
         self._is_overflow = not self._stepped
 
-    def _fused_step(self) -> bool:
+    def _plan(self):
         if not self._fused_plan_tried:
             self._fused_plan_tried = True
             if self.accelerator_state.device.type == "cuda":
@@ -295,14 +313,69 @@ class AcceleratedOptimizer(torch.optim.Optimizer):
         plan = self._fused_plan
         if plan is not None and plan.signature != FusedAdamPlan._signature(self.optimizer):
             self._fused_plan = plan = FusedAdamPlan.try_build(self.optimizer)  # add_param_group() happened
-        if plan is None or _has_step_hooks(self.optimizer) or not plan.step():
+        if plan is None or _has_step_hooks(self.optimizer):
+            return None
+        return plan
+
+    def _fused_step(self) -> bool:
+        plan = self._plan()
+        if plan is None or not plan.step():
             return False
         # torch's LRScheduler patches optimizer.step to learn that a step happened before scheduler.step()
         self.optimizer._opt_called = True
         return True
 
+    def _fused_scaled_step(self) -> bool:
+        """fp16 (reference optimizer.py:163-177: ``scaler.step(optimizer)`` + ``scaler.update()``): the unscale comes
+        from the allreduce statistics, the Adam kernel applies ``1/scale`` (and a pending clip coefficient) on the
+        fly and returns at once when the device-side found-inf flag is set, and ``scaler.update()`` adjusts the scale
+        on the device.  torch's ``scaler.step`` reads the flag on the host (``.item()``) to decide whether to call
+        ``optimizer.step``; here nothing waits for the GPU.  Whether the step was skipped is settled lazily — when
+        ``step_was_skipped`` is read (schedulers do) or at the next step — from a pinned copy of the flag."""
+        from torch.amp.grad_scaler import OptState
+
+        scaler = self.scaler
+        plan = self._plan() if scaler.is_enabled() else None
+        if plan is None:
+            return False
+        state = scaler._per_optimizer_states[id(self.optimizer)]
+        if state["stage"] is OptState.STEPPED:
+            raise RuntimeError("step() has already been called since the last update().")
+        if state["stage"] is OptState.READY:
+            scaler.unscale_(self.optimizer)  # fused: statistics -> found_inf; the multiply stays pending
+        found = list(state["found_inf_per_device"].values())
+        if len(found) != 1 or found[0].device != plan.device:
+            return False  # scaler.step() below finds the gradients already unscaled and takes torch's route
+        found_inf = found[0]
+        if not plan.step(found_inf=found_inf):
+            return False
+        state["stage"] = OptState.STEPPED
+        # async copy of the flag; the event completes long before anybody asks
+        if self._skip_host is None:
+            self._skip_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        self._skip_host.copy_(found_inf.reshape(1), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._skip_pending = (ev, plan.last_steps)
+        scaler.update()
+        self.optimizer._opt_called = True
+        return True
+
+    def _settle_skip(self):
+        """Resolve the previous fused step: if the device skipped it, take the optimistic `step` increment back."""
+        pending, self._skip_pending = self._skip_pending, None
+        if pending is None:
+            return
+        ev, steps = pending
+        ev.synchronize()
+        skipped = bool(self._skip_host.item() != 0.0)
+        if skipped and steps:
+            torch._foreach_sub_(steps, 1)
+        self._is_overflow = skipped
+
     @property
     def step_was_skipped(self) -> bool:
+        self._settle_skip()
         return self._is_overflow
 
     def _switch_parameters(self, parameters_map):
@@ -310,10 +383,13 @@ class AcceleratedOptimizer(torch.optim.Optimizer):
             group["params"] = [parameters_map.get(p, p) for p in group["params"]]
 
     def __getstate__(self):
-        drop = {"_inner_step", "_probed_step", "_fused_plan"}
+        self._settle_skip()
+        drop = {"_inner_step", "_probed_step", "_fused_plan", "_skip_pending", "_skip_host"}
         return {k: v for k, v in self.__dict__.items() if k not in drop}
 
     def __setstate__(self, state):
         self.__dict__.update(state)
+        self._skip_pending = self._skip_host = None
+        self._fused_plan = None
         if self.scaler is not None:
             self._arm_step_probe()

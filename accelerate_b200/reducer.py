@@ -44,9 +44,12 @@ import torch.distributed as dist
 from torch.autograd import Variable
 from torch.distributed.algorithms.join import Join, Joinable, JoinHook
 
-from . import native
-
+import sys
+import threading
 import weakref
+
+from . import lazy_grad, native
+from .lazy_grad import raw_grad, raw_set_grad
 
 _ALIGN = 32  # bytes: every parameter slice / bucket starts on a 32-byte boundary (16 B in the half-width wire copy)
 _LIVE = weakref.WeakSet()
@@ -185,7 +188,9 @@ class GradReducer:
         self._graveyard = []
         self._comm_dirty = False
         self._wire_dirty = False
-        self._pending_mult = None
+        self._pending_mult = None  # lazy_grad.PendingScale of a deferred clip
+        self._stats_versions = []
+        self._closed = False
         self._locally_undefined = []  # (bucket, i) whose gradient was None when an unused parameter was filled in
         self._shadowing = False  # inside shadow_backward (a joined rank standing in for a backward it does not run)
         self.user_hook = None  # (state, hook): a user-supplied communication algorithm replaces the fused kernel
@@ -275,18 +280,24 @@ class GradReducer:
 
         def hook(param):
             if not self._armed:
+                # a gradient changed outside a reduction (second backward without a forward, no_sync micro-step):
+                # the statistics of the last reduction no longer describe the buffer
+                self.stats_valid = False
                 return
             if not self._cb_queued:
+                # end-of-backward callback of the graph task this hook runs in.  Under reentrant activation
+                # checkpointing that may be a NESTED task; `_on_graph_task_end` then declines and the next hook
+                # (in the enclosing task) queues again.
                 self._cb_queued = True
-                Variable._execution_engine.queue_callback(self._finalize_backward)
+                Variable._execution_engine.queue_callback(self._on_graph_task_end)
             if seen[i]:
                 return  # same parameter fired twice in one backward (retain_graph replays): count once
             seen[i] = True
-            g = param.grad
+            g = raw_grad(param)
             if g is not view and g is not None and g.data_ptr() != ptr:
                 # autograd put this gradient somewhere else: adopt it into the fusion buffer
                 bucket.staged.append((i, g if g.is_contiguous() else g.contiguous()))
-                param.grad = view
+                raw_set_grad(param, view)
             bucket.pending -= 1
             if bucket.pending == 0:
                 self._launch_ready()
@@ -392,7 +403,10 @@ class GradReducer:
     def _pick_algo(self, seg):
         algo = self.algo
         if algo == native.ALGO_AUTO:
-            algo = native.ALGO_NVLS if (seg.multicast and self.world >= _NVLS_MIN_WORLD) else native.ALGO_TWOSHOT
+            # the switch adds the N raw copies and the kernel scales the sum; that equals the oracle's
+            # sum_r fl(g_r * 1/N) exactly only when 1/N is a power of two, so other world sizes keep the two-shot
+            pow2 = self.world & (self.world - 1) == 0
+            algo = native.ALGO_NVLS if (seg.multicast and pow2 and self.world >= _NVLS_MIN_WORLD) else native.ALGO_TWOSHOT
         return algo
 
     def blocks_for(self, algo: int) -> int:
@@ -432,8 +446,42 @@ class GradReducer:
             g.wire_flat = g.wire.tensor(dtype, g.total_elems)
             g.wire_native = self._native_dtype(dtype)
 
+    @staticmethod
+    def _inside_nested_backward() -> bool:
+        """True when the graph task whose final callbacks are running was started from inside another backward
+        (``torch.utils.checkpoint(use_reentrant=True)`` re-runs autograd from a Function's backward).  The engine
+        offers no query for that, but the Python stack does: a nested task is driven by a ``torch.autograd.backward``
+        call, so an ``_engine_run_backward`` frame sits below this callback — one more than the outermost task has
+        (none on the engine's own device threads, one on a Python thread that called ``backward`` itself)."""
+        code = torch.autograd.graph._engine_run_backward.__code__
+        depth, frame = 0, sys._getframe(1)
+        while frame is not None:
+            if frame.f_code is code:
+                depth += 1
+            frame = frame.f_back
+        baseline = 0 if isinstance(threading.current_thread(), threading._DummyThread) else 1
+        return depth > baseline
+
+    def _on_graph_task_end(self):
+        """Final callback of the graph task in which a gradient hook fired (torch's Reducer queues its finalizer when
+        the last bucket is ready, reducer.cpp mark_variable_ready; we also need the end of a backward that left
+        parameters unused, so the callback is queued early and decides here)."""
+        if not self._armed:
+            return
+        if self._next < len(self.buckets) and self._inside_nested_backward():
+            self._cb_queued = False  # the enclosing backward continues: its next hook queues the callback again
+            return
+        self._finalize_backward()
+
+    def finish_open_backward(self):
+        """Safety net for a backward whose last gradient hook ran in a nested graph task that could not know it was
+        the last (reentrant checkpointing + parameters left unused): finish the reduction before anybody consumes
+        the gradients.  A no-op in every ordinary run."""
+        if self._armed and not self._cb_queued and any(any(b.seen) for b in self.buckets):
+            self._finalize_backward()
+
     def _finalize_backward(self):
-        """Autograd-engine callback: runs once, after the last gradient of this backward."""
+        """Runs once per sync backward, after its last gradient."""
         try:
             if self._next < len(self.buckets):
                 self._handle_unready()
@@ -461,6 +509,9 @@ class GradReducer:
                 self._graveyard.clear()
                 self.stats_valid = self.user_hook is None  # a user hook bypasses the kernel that gathers them
                 self.unscaled = False
+                # the native kernels do not touch torch's version counters; anything that writes a gradient through
+                # torch afterwards (p.grad.mul_(), a second backward accumulating into the views) does
+                self._stats_versions = [g.flat._version for g in self.groups.values()]
             if self.find_unused_parameters:
                 self._restore_globally_unused()
             self.num_reductions += 1
@@ -485,14 +536,14 @@ class GradReducer:
         # if NO rank used the parameter (`_restore_globally_unused`)
         for b, i in missing:
             p, view = b.params[i], b.views[i]
-            g = p.grad
+            g = raw_grad(p)
             if g is None:
                 view.zero_()
                 self._locally_undefined.append((b, i))
-                p.grad = view
+                raw_set_grad(p, view)
             elif g.data_ptr() != b.ptrs[i]:
                 b.staged.append((i, g if g.is_contiguous() else g.contiguous()))
-                p.grad = view
+                raw_set_grad(p, view)
             b.seen[i] = True
             b.pending -= 1
         self._launch_ready()
@@ -517,7 +568,7 @@ class GradReducer:
             used = used.tolist()
             undefined = [(b, i) for b, i in undefined if used[index[id(b.params[i])]] == 0]
         for b, i in undefined:
-            b.params[i].grad = None
+            raw_set_grad(b.params[i], None)
 
     def shadow_backward(self):
         """A rank that ran out of data (torch ``Join``) stands in for one sync backward of the others: it contributes
@@ -549,9 +600,15 @@ class GradReducer:
     # ------------------------------------------------------------------ API the wrapper / Accelerator use
     def prepare_for_backward(self, unused=None):
         """Arm the next backward (torch Reducer::prepare_for_backward; reached from accelerator.py:1222)."""
+        self.finish_open_backward()
+        if self._pending_mult is not None:
+            # a deferred clip that no fused optimizer step consumed: the gradients may be kept (accumulation without
+            # zero_grad), so they must carry the coefficient before new ones are added — what the reference's
+            # in-place clip left behind
+            self._pending_mult.apply()
+            self._pending_mult = None
         self._armed = True
         self.stats_valid = False
-        self._pending_mult = None  # a deferred clip that no optimizer step consumed dies with its gradients
         if self.is_cuda:
             self.compute_stream = torch.cuda.current_stream(self.device).cuda_stream
         self._reset_iteration()
@@ -560,10 +617,16 @@ class GradReducer:
         """Every managed parameter's ``.grad`` is (still) its view into the fusion buffer."""
         for b in self.buckets:
             for p, ptr in zip(b.params, b.ptrs):
-                g = p.grad
+                g = raw_grad(p)
                 if g is None or g.data_ptr() != ptr:
                     return False
         return True
+
+    def stats_fresh(self) -> bool:
+        """The statistics of the last reduction still describe the fusion buffer: nothing wrote a gradient through
+        torch since (the views share their version counter with the flat buffer)."""
+        return (self.is_cuda and self.stats_valid
+                and self._stats_versions == [g.flat._version for g in self.groups.values()])  # fmt: skip
 
     def effective_algo(self) -> str:
         """"nvls" or "twoshot": what the bucket kernels of this reducer actually run."""
@@ -575,7 +638,7 @@ class GradReducer:
     def manages(self, parameters) -> bool:
         """True iff ``parameters`` (those with grads) are exactly this reducer's parameters and their
         gradients live in its buffers — the precondition for using the fused statistics."""
-        ids = {id(p) for p in parameters if p.grad is not None}
+        ids = {id(p) for p in parameters if raw_grad(p) is not None}
         return ids == self._managed_ids and self.grads_in_buffer()
 
     def fused_clip_(self, max_norm: float, norm_type: float = 2.0, scale: torch.Tensor | None = None, defer: bool = False):
@@ -596,27 +659,39 @@ class GradReducer:
         out = torch.empty(3, dtype=torch.float32, device=self.device)
         scale_ptr = scale.data_ptr() if scale is not None else None
         ctx.finalize_norm(self.slot_base, len(self.buckets), True, norm_type, max_norm, scale_ptr, out.data_ptr(), st)
-        if scale is not None and self.unscaled:
+        # an earlier unscale-only multiplier that nobody materialised yet is superseded: `out[1]` = 1/S * coef
+        earlier, self._pending_mult = self._pending_mult, None
+        still_scaled = earlier is not None and earlier.consume()
+        if scale is not None and self.unscaled and not still_scaled:
             # gradients already carry 1/S: keep only the clip coefficient (exact for power-of-two S)
             out[1].mul_(scale.to(torch.float32).reshape(()))
-        mult_ptr = out.data_ptr() + 4
-        if defer and scale is None:
-            # fused optimizer consumption: the Adam kernel multiplies on the fly; p.grad keeps the UNCLIPPED values
-            self._pending_mult = out
+        if defer:
+            # fused optimizer consumption: the multiplier stays pending; the fused Adam kernel
+            # applies it on the fly, anything else that looks at a gradient first triggers the pass (lazy_grad.py)
+            self._pending_mult = lazy_grad.defer(out, lambda: self._apply_multiplier(out), owner=self)
         else:
-            for group in self.groups.values():
-                ctx.scale_flat(group.flat.data_ptr(), group.total_elems, group.native_dtype, mult_ptr, 0, st)
+            self._apply_multiplier(out)
         if scale is not None:
             self.unscaled = True
         if max_norm >= 0:
             self.stats_valid = False  # the buffer no longer holds the values the statistics describe
         return out
 
+    def _apply_multiplier(self, out: torch.Tensor):
+        """One multiply pass over the fusion buffer by ``out[1]`` (device-side; exits at once when it is 1)."""
+        if self._closed:
+            return
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        for group in self.groups.values():
+            self.rt.ctx.scale_flat(group.flat.data_ptr(), group.total_elems, group.native_dtype, out.data_ptr() + 4, 0, st)
+
     def take_pending_multiplier(self):
-        """The [total_norm, multiplier, found_inf] tensor of a deferred clip (B200DP_DEFER_CLIP=1), handed to the
-        fused optimizer step exactly once."""
+        """The pending [total_norm, multiplier, found_inf] tensor of a deferred clip / unscale, handed to the fused
+        optimizer step exactly once (None if there is none or it was already applied)."""
         pending, self._pending_mult = self._pending_mult, None
-        return pending
+        if pending is None or not pending.consume():
+            return None
+        return pending.out
 
     def clamp_(self, clip_value: float):
         st = torch.cuda.current_stream(self.device).cuda_stream
@@ -630,7 +705,8 @@ class GradReducer:
             return False
         for b in self.buckets:
             for p, ptr in zip(b.params, b.ptrs):
-                if p.grad is not None and p.grad.data_ptr() == ptr:
+                g = raw_grad(p)
+                if g is not None and g.data_ptr() == ptr:
                     return False
         return True
 
@@ -681,6 +757,43 @@ class GradReducer:
         for h in self._hooks:
             h.remove()
         self._hooks = []
+
+    def close(self):
+        """Release everything the reducer took from the runtime: autograd hooks, the symmetric fusion / wire
+        segments and the statistics slots (``Accelerator.free_memory``; the reference's DDP wrapper frees its buckets
+        when it is garbage collected).  Gradients that were views of the fusion buffer are detached into ordinary
+        tensors first.  Every rank is expected to close its reducers in the same order (slot numbering is
+        positional), like every other collective-ordering rule of this class."""
+        if self._closed:
+            return
+        self.remove_hooks()
+        if self._pending_mult is not None:
+            self._pending_mult.apply()
+            self._pending_mult = None
+        self._closed = True
+        self._armed = False
+        self.stats_valid = False
+        _LIVE.discard(self)
+        if not self.is_cuda:
+            return
+        with torch.no_grad():
+            for b in self.buckets:
+                for p, ptr in zip(b.params, b.ptrs):
+                    g = raw_grad(p)
+                    if g is not None and g.data_ptr() == ptr:
+                        raw_set_grad(p, g.clone())
+        torch.cuda.synchronize(self.device)
+        for group in self.groups.values():
+            group.flat = None
+            group.wire_flat = None
+            for seg_name in ("segment", "wire"):
+                seg = getattr(group, seg_name)
+                if seg is not None:
+                    self.rt.free_segment(seg)
+                    setattr(group, seg_name, None)
+        for b in self.buckets:
+            b.flat, b.views = None, []
+        self.rt.release_slots(self.slot_base, len(self.buckets))
 
 
 class _B200JoinHook(JoinHook):
@@ -752,6 +865,7 @@ class B200DataParallel(torch.nn.Module, Joinable):
         self._ddp_buffers = [b for b in module.buffers() if b is not None]
         # rank 0's weights (and buffers) become everyone's (torch: _sync_module_states)
         self.reducer.broadcast_parameters(params)
+        self._broadcast_frozen(0)
         self._sync_buffers()
 
     # ---- DDP surface ----
@@ -790,6 +904,16 @@ class B200DataParallel(torch.nn.Module, Joinable):
                 raise RuntimeError("register_comm_hook can only be called once.")
         else:
             self.reducer.set_user_hook(state, hook)
+
+    def _broadcast_frozen(self, src: int):
+        """torch's ``_sync_module_states`` makes EVERY parameter equal to the source rank's, trainable or not; the
+        frozen ones have no slot in the fusion buffer and go through the staged broadcast."""
+        frozen = [p.data for p in self.module.parameters() if not p.requires_grad]
+        if frozen and self.reducer.world > 1:
+            from .utils.operations import broadcast
+
+            with torch.no_grad():
+                broadcast(frozen, from_process=src)
 
     def _will_sync_buffers(self) -> bool:
         return bool(self._ddp_buffers) and self.broadcast_buffers and self.require_forward_param_sync
@@ -846,6 +970,7 @@ class B200DataParallel(torch.nn.Module, Joinable):
         """Leaving the Join context: everyone adopts the model of the rank that trained longest."""
         src = self._find_common_rank(is_last_joiner)
         self.reducer.broadcast_parameters(self.reducer.params, src=src)
+        self._broadcast_frozen(src)
         if self.broadcast_buffers:
             self._broadcast_buffers(src)
 

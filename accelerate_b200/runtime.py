@@ -176,11 +176,38 @@ class SymmRuntime:
 
     # ------------------------------------------------------------------ slots
     def reserve_slots(self, n: int) -> int:
+        """``n`` consecutive statistics slots.  Released ranges are reused first-fit; every rank makes the same
+        sequence of reserve / release calls, so slot numbers agree across ranks."""
+        free = self.__dict__.setdefault("_slot_free", [])
+        for k, (base, size) in enumerate(free):
+            if size >= n:
+                if size == n:
+                    free.pop(k)
+                else:
+                    free[k] = (base + n, size - n)
+                return base
         base = self._slot_next
         if base + n > native.MAX_SLOTS:
             raise native.B200dpError(f"out of stats slots ({native.MAX_SLOTS})")
         self._slot_next += n
         return base
+
+    def release_slots(self, base: int, n: int):
+        if n <= 0:
+            return
+        if base + n == self._slot_next:
+            self._slot_next = base
+            return
+        free = self.__dict__.setdefault("_slot_free", [])
+        free.append((base, n))
+        free.sort()
+        merged = []
+        for b, s_ in free:  # coalesce neighbours
+            if merged and merged[-1][0] + merged[-1][1] == b:
+                merged[-1] = (merged[-1][0], merged[-1][1] + s_)
+            else:
+                merged.append((b, s_))
+        self._slot_free = merged
 
     # ------------------------------------------------------------------ segments
     def _recv_fd(self, serial: int, src: int, mc: bool) -> int:
@@ -254,10 +281,16 @@ class SymmRuntime:
         return self._all_ok(ok)
 
     def free_segment(self, s: Segment):
+        """Unmap and release this rank's part of a symmetric segment.  cuMem allocations are reference counted by
+        their mappings, so a peer that still has this memory mapped keeps the physical pages alive until it frees
+        its own side: no cross-rank barrier is needed (cudaIpc segments — the fallback kind — do need one)."""
         torch.cuda.synchronize(self.device)
-        self._barrier()
+        if self.kind != native.HANDLE_POSIXFD:
+            self._barrier()
         s.bytes_u8 = None
         self.ctx.seg_destroy(s.seg)
+        if s is self.staging:
+            self.staging = None
 
     def ensure_staging(self) -> Segment:
         if self.staging is None:

@@ -15,21 +15,26 @@ import types
 
 import torch
 
+from . import lazy_grad
+from .lazy_grad import raw_grad
 from .reducer import live_reducers
 
 
 class FusedGradScaler(torch.amp.GradScaler):
     def _unscale_grads_(self, optimizer, inv_scale, found_inf, allow_fp16):
-        params = [p for group in optimizer.param_groups for p in group["params"] if p.grad is not None]
+        params = [p for group in optimizer.param_groups for p in group["params"] if raw_grad(p) is not None]
         ids = {id(p) for p in params}
         fused = []
         for red in live_reducers():
-            if red.is_cuda and red.stats_valid and not red.unscaled and red._managed_ids <= ids and red.grads_in_buffer():
+            red.finish_open_backward()
+            if red.is_cuda and red.stats_fresh() and not red.unscaled and red._managed_ids <= ids and red.grads_in_buffer():
                 fused.append(red)
         result = {}
         covered = set()
         for red in fused:
-            out = red.fused_clip_(-1.0, 2.0, scale=self._scale)  # multiply by 1/scale, report found_inf
+            # 1/scale becomes a pending multiplier (the fused Adam step applies it on the fly; any other reader of a
+            # gradient triggers the pass first), found_inf comes from the allreduce statistics
+            out = red.fused_clip_(-1.0, 2.0, scale=self._scale, defer=lazy_grad.enabled())
             found_inf.copy_(torch.maximum(found_inf, out[2].to(found_inf.device)))
             covered |= red._managed_ids
             result[found_inf.device] = found_inf

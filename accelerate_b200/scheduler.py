@@ -39,7 +39,9 @@ class AcceleratedScheduler:
         if not self.step_with_optimizer:
             inner.step(*args, **kwargs)
             return
-        budget = getattr(inner, "total_steps", None)  # OneCycle-style schedulers must not overrun their length
+        # OneCycle-style schedulers must not overrun their length when each step advances num_processes times; with
+        # split batches the reference steps unconditionally (scheduler.py:70-82)
+        budget = None if self.split_batches else getattr(inner, "total_steps", None)
         for _ in range(self._times_to_advance()):
             if budget is None or inner._step_count <= budget:
                 inner.step(*args, **kwargs)

@@ -293,6 +293,7 @@ class AcceleratorState(_Borg):
         if PartialState._shared == {}:
             PartialState(cpu, **kwargs)
         self.__dict__.update(PartialState._shared)
+        self._check_initialized(mixed_precision, cpu)  # a second, differently configured Accelerator raises (state.py:913)
         if not self.initialized:
             if mixed_precision is None:
                 mixed_precision = parse_choice_from_env("ACCELERATE_MIXED_PRECISION", "no")

@@ -16,7 +16,44 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def adam_full_size():
+    """The fused Adam/AdamW step at the HEADLINE size: GPT-2-medium's 292 parameter tensors (354,823,168 elements,
+    loose gradients), one launch = 28 B x 354.8 M = 9.93 GB of algorithmic traffic.
+
+        ncu --set full --clock-control none --import-source on -k regex:multi_adam -s 1 -c 1 \
+            -o gpurun_out/r02_multi_adam python benchmarks/kernel_probe.py --adam
+    """
+    from transformers import GPT2Config, GPT2LMHeadModel
+
+    from accelerate_b200.state import PartialState
+
+    rt = PartialState().runtime
+    st = torch.cuda.current_stream().cuda_stream
+    with torch.device("meta"):
+        shapes = [tuple(p.shape) for p in GPT2LMHeadModel(GPT2Config(n_embd=1024, n_layer=24, n_head=16)).parameters()]
+    params = [torch.randn(s, device=rt.device) * 0.02 for s in shapes]
+    grads = [torch.randn(s, device=rt.device) * 1e-3 for s in shapes]
+    numels = [p.numel() for p in params]
+    assert sum(numels) == 354_823_168, sum(numels)
+    moffs, total = [], 0
+    for k in numels:
+        moffs.append(total)
+        total += (k + 3) & ~3
+    m_flat = torch.zeros(total, device=rt.device)
+    v_flat = torch.zeros(total, device=rt.device)
+    table = rt.ctx.make_adam_table([p.data_ptr() for p in params], numels, moffs, [g.data_ptr() for g in grads])
+    mult = torch.tensor([0.7], device=rt.device)
+    for rep in range(3):
+        rt.ctx.multi_adam(table, m_flat.data_ptr(), v_flat.data_ptr(), 1 - 1e-4 * 0.01, 0.0, 0.9, 0.999, -1e-4 / (1 - 0.9 ** (rep + 1)),
+                          (1 - 0.999 ** (rep + 1)) ** 0.5, 1e-8, mult.data_ptr(), None, st)  # fmt: skip
+    torch.cuda.synchronize()
+    rt.ctx.check_status()
+    print("adam probe ok", sum(numels), "elements")
+
+
 def main():
+    if "--adam" in sys.argv:
+        return adam_full_size()
     from accelerate_b200 import native
     from accelerate_b200.state import PartialState
 

@@ -28,15 +28,27 @@ class Net(torch.nn.Module):
         self.gain = torch.nn.Parameter(torch.ones(16, dtype=torch.bfloat16))  # a second gradient dtype (own buckets)
         self.side = torch.nn.Linear(16, 16)  # only used when `branch` says so (find_unused_parameters runs)
         self.branch = 0
+        # reentrant activation checkpointing (HF gradient_checkpointing_enable() in many releases): the checkpointed
+        # segments re-run autograd from inside a Function's backward, so gradient hooks fire in NESTED graph tasks —
+        # the first one of a backward included (the tail segment is the first thing backward reaches)
+        self.ckpt = os.environ.get("DDP_DIFF_CKPT", "0") == "1"
+
+    def _mid(self, h):
+        return self.fc(torch.tanh(self.fc(h)))  # one module applied twice: its gradients accumulate inside one backward
+
+    def _tail(self, h):
+        return self.bn(h + 0.1 * self.frozen(h)) * self.gain.float()
 
     def forward(self, ids):
+        from torch.utils.checkpoint import checkpoint
+
         h = self.norm(self.emb(ids)).mean(dim=1)
-        h = self.fc(torch.tanh(self.fc(h)))  # one module applied twice: its gradients accumulate inside one backward
+        h = checkpoint(self._mid, h, use_reentrant=True) if self.ckpt else self._mid(h)
         if self.branch == 1:
             h = h + self.side(h)
         elif self.branch == 2:  # skips `fc` entirely on top of it
             h = self.side(self.norm(self.emb(ids)).mean(dim=1))
-        h = self.bn(h + 0.1 * self.frozen(h)) * self.gain.float()
+        h = checkpoint(self._tail, h, use_reentrant=True) if self.ckpt else self._tail(h)
         return self.head(h)
 
 

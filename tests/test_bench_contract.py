@@ -24,7 +24,8 @@ def test_reference_arm_json_line():
                 "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):  # fmt: skip
         assert key in line, key
     assert line["impl"] == "reference" and line["metric"] == "samples_per_sec" and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    # "reference" when baseline/_ref (pip install --target of /root/reference) is present, else the oracle port
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert line["vs_baseline"] is None  # BASELINE.md publishes no number for this metric
 

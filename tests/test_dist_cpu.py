@@ -54,6 +54,15 @@ def test_differential_against_torch_ddp(seed, unused, hook):
     assert out.count("DDP_DIFF_OK") == 2, out[-3000:]
 
 
+def test_differential_against_torch_ddp_reentrant_checkpointing():
+    """with ``checkpoint(use_reentrant=True)`` the first gradient hook of a backward fires inside a
+    nested graph task; the end-of-backward finalizer must wait for the OUTER task.  Same random action sequence as
+    above, two checkpointed segments, bit-equal to torch DDP."""
+    out = run_distributed("dist_ddp_diff.py", 2, timeout=300, env={"DDP_DIFF_SEED": "13", "DDP_DIFF_UNUSED": "0", "DDP_DIFF_HOOK": "",
+                               "DDP_DIFF_NO_BCAST": "0", "DDP_DIFF_CKPT": "1"})  # fmt: skip
+    assert out.count("DDP_DIFF_OK") == 2, out[-3000:]
+
+
 @pytest.mark.parametrize("world,find_unused", [(2, "0"), (2, "1"), (4, "0")])
 def test_join_uneven_inputs_matches_torch_ddp(world, find_unused):
     """torch's Join context (behind the reference's join_uneven_inputs): ranks train 3+2r iterations, early finishers

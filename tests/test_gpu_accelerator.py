@@ -318,3 +318,210 @@ def test_fused_adam_loose_gradients_single_process(cls):
     for p, q in zip(model.parameters(), ref.parameters()):
         assert_tracks_torch(p, q, 2e-3, "fallback step")
     rt.ctx.check_status()
+
+
+def test_deferred_clip_is_invisible_and_consumed_by_the_fused_step(monkeypatch):
+    """VERDICT r1 #6 / SURVEY.md §8f row 1: by default ``clip_grad_norm_`` leaves the coefficient pending
+    (accelerate_b200/lazy_grad.py).  (a) The fused AdamW step consumes it: no scale pass is launched and the update
+    equals torch's clip + AdamW.  (b) Anything that looks at ``p.grad`` first sees the reference's clipped values
+    (the pass is triggered by the access) and the following step is still right.  (c) A non-fused optimizer gets
+    clipped gradients too."""
+    from accelerate_b200 import Accelerator, B200DataParallel, lazy_grad
+    from accelerate_b200.state import PartialState
+
+    monkeypatch.delenv("B200DP_DEFER_CLIP", raising=False)
+    acc = Accelerator()
+    model, ref = mlp(7), mlp(7)
+    ddp = B200DataParallel(model, device_ids=[0], bucket_cap_mb=0.02)
+    opt = acc.prepare(torch.optim.AdamW(model.parameters(), lr=2e-3))
+    ref_opt = torch.optim.AdamW(ref.parameters(), lr=2e-3, foreach=True)
+    rt = PartialState().runtime
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for step in range(4):
+        x = torch.randn(8, 64, device="cuda", generator=g)
+        ddp(x).square().mean().backward()
+        ref(x).square().mean().backward()
+        tn = acc.clip_grad_norm_(ddp.parameters(), 0.05)
+        ref_tn = torch.nn.utils.clip_grad_norm_(ref.parameters(), 0.05)
+        assert acc.last_clip_mode == "fused" and torch.allclose(tn, ref_tn, rtol=1e-5)
+        assert lazy_grad.has_pending(), "the multiply pass must not have run yet"
+        launches = rt.ctx.launches
+        if step % 2 == 1:  # (b) observe the gradients before the step
+            for p, q in zip(model.parameters(), ref.parameters()):
+                assert torch.allclose(p.grad, q.grad, rtol=1e-5, atol=1e-10)
+            assert not lazy_grad.has_pending() and rt.ctx.launches - launches == 1, "exactly one scale_flat pass"
+            launches = rt.ctx.launches
+        opt.step()
+        assert not lazy_grad.has_pending()
+        assert rt.ctx.launches - launches == 1, "only the fused Adam launch: the clip multiplier rides along"
+        ref_opt.step()
+        opt.zero_grad(set_to_none=step < 2)
+        ref_opt.zero_grad()
+        for p, q in zip(model.parameters(), ref.parameters()):
+            assert_tracks_torch(p, q, 2e-3, step)
+    # gradients kept across steps (no zero_grad): the pending coefficient must be in them before the next backward adds
+    x = torch.randn(8, 64, device="cuda", generator=g)
+    for m in (ddp, ref):
+        m(x).square().mean().backward()
+    acc.clip_grad_norm_(ddp.parameters(), 0.05)
+    torch.nn.utils.clip_grad_norm_(ref.parameters(), 0.05)
+    for m in (ddp, ref):  # second backward accumulates on top of the clipped gradients
+        m(x).square().mean().backward()
+    for p, q in zip(model.parameters(), ref.parameters()):
+        assert torch.allclose(p.grad, q.grad, rtol=1e-5, atol=1e-10)
+    # (c) a plain SGD step reads p.grad from Python -> clipped values
+    sgd = acc.prepare(torch.optim.SGD(model.parameters(), lr=0.1))
+    ref_sgd = torch.optim.SGD(ref.parameters(), lr=0.1)
+    opt.zero_grad()
+    ref_opt.zero_grad()
+    for m in (ddp, ref):
+        m(x).square().mean().backward()
+    acc.clip_grad_norm_(ddp.parameters(), 0.05)
+    torch.nn.utils.clip_grad_norm_(ref.parameters(), 0.05)
+    sgd.step()
+    ref_sgd.step()
+    for p, q in zip(model.parameters(), ref.parameters()):
+        assert_tracks_torch(p, q, 2e-3, "sgd after deferred clip")
+    rt.ctx.check_status()
+
+
+def test_deferred_clip_loose_gradients_single_process(monkeypatch):
+    """The same laziness without a reducer (world size 1): multi_stats + finalize, the multi_scale pass stays pending and
+    the loose-layout fused AdamW consumes it."""
+    from accelerate_b200 import Accelerator, lazy_grad
+    from accelerate_b200.state import PartialState
+
+    monkeypatch.delenv("B200DP_DEFER_CLIP", raising=False)
+    acc = Accelerator()
+    model, ref = mlp(9), mlp(9)
+    opt = torch.optim.AdamW(model.parameters(), lr=2e-3)
+    ref_opt = torch.optim.AdamW(ref.parameters(), lr=2e-3, foreach=True)
+    model, opt = acc.prepare(model, opt)
+    rt = PartialState().runtime
+    g = torch.Generator(device="cuda").manual_seed(4)
+    for step in range(3):
+        x = torch.randn(8, 64, device="cuda", generator=g)
+        acc.backward(model(x).square().mean())
+        ref(x).square().mean().backward()
+        tn = acc.clip_grad_norm_(model.parameters(), 0.05)
+        ref_tn = torch.nn.utils.clip_grad_norm_(ref.parameters(), 0.05)
+        assert acc.last_clip_mode == "multi_tensor" and torch.allclose(tn, ref_tn, rtol=1e-5)
+        assert lazy_grad.has_pending()
+        launches = rt.ctx.launches
+        if step == 1:
+            for p, q in zip(model.parameters(), ref.parameters()):
+                assert torch.allclose(p.grad, q.grad, rtol=1e-5, atol=1e-10)
+            launches = rt.ctx.launches
+        opt.step()
+        assert not lazy_grad.has_pending() and rt.ctx.launches - launches == 1
+        ref_opt.step()
+        opt.zero_grad()
+        ref_opt.zero_grad()
+        for p, q in zip(model.parameters(), ref.parameters()):
+            assert_tracks_torch(p, q, 2e-3, step)
+
+
+def test_stale_statistics_are_not_trusted():
+    """the fused clip may use the allreduce statistics only while they describe the buffer.  A
+    gradient edited through torch (``p.grad.mul_``), or a second backward accumulating into the views, bumps the
+    fusion buffer's version counter: the clip must then recompute the norm from the live gradients."""
+    from accelerate_b200 import Accelerator, B200DataParallel
+
+    acc = Accelerator()
+    model = mlp(11)
+    ddp = B200DataParallel(model, device_ids=[0], bucket_cap_mb=0.02)
+    x = torch.randn(8, 64, device="cuda")
+    ddp(x).square().mean().backward()
+    with torch.no_grad():
+        for p in model.parameters():
+            p.grad.mul_(3.0)
+    ref_tn, ref = torch_clip_reference([p.grad for p in model.parameters()], 0.05)
+    tn = acc.clip_grad_norm_(ddp.parameters(), 0.05)
+    assert acc.last_clip_mode == "multi_tensor", "stale statistics must not be used"
+    assert torch.allclose(tn, ref_tn, rtol=1e-5)
+    for p, r in zip(model.parameters(), ref):
+        assert torch.allclose(p.grad, r, rtol=1e-5, atol=1e-10)
+    # a second backward without a forward accumulates into the views
+    for p in model.parameters():
+        p.grad = None
+    out = ddp(x).square().mean()
+    out.backward(retain_graph=True)
+    out.backward()
+    ref_tn, ref = torch_clip_reference([p.grad for p in model.parameters()], 0.05)
+    tn = acc.clip_grad_norm_(ddp.parameters(), 0.05)
+    assert acc.last_clip_mode == "multi_tensor" and torch.allclose(tn, ref_tn, rtol=1e-5)
+
+
+def test_free_memory_releases_segments_and_slots():
+    """``Accelerator.free_memory()`` + re-prepare (the find_executable_batch_size pattern) must
+    not leak the gradient-sized symmetric buffer or the statistics slots."""
+    from accelerate_b200 import Accelerator, B200DataParallel
+    from accelerate_b200.state import PartialState
+
+    acc = Accelerator()
+    rt = PartialState().runtime
+    x = torch.randn(8, 64, device="cuda")
+    slots0 = rt._slot_next
+    seg_ids = []
+    for attempt in range(4):
+        model = mlp(attempt)
+        ddp = B200DataParallel(model, device_ids=[0], bucket_cap_mb=0.02)
+        acc._wrappers.append(ddp)
+        ddp(x).square().mean().backward()
+        kept = [p.grad.clone() for p in model.parameters()]
+        seg_ids.append(next(iter(ddp.reducer.groups.values())).segment.seg)
+        assert ddp.reducer.slot_base == slots0, "slots of the closed reducer are reused"
+        acc.free_memory()
+        assert rt._slot_next == slots0
+        for p, k in zip(model.parameters(), kept):  # gradients survive as ordinary tensors
+            assert torch.equal(p.grad, k)
+    assert len(set(seg_ids)) == 1, f"segment table slot must be reused, got {seg_ids}"
+    rt.ctx.check_status()
+
+
+def test_fp16_fused_adam_step_skips_on_device(monkeypatch):
+    """VERDICT r1 #8 (reference optimizer.py:163-177): under a GradScaler the fused Adam kernel reads found-inf on the
+    device — no host sync in ``step`` — and the skipped step is settled lazily.  Parameters, `step` counters, the
+    loss scale and ``step_was_skipped`` follow torch's GradScaler + AdamW over a sequence with an overflow."""
+    from accelerate_b200 import Accelerator, B200DataParallel, GradScalerKwargs, lazy_grad
+    from accelerate_b200.state import PartialState
+
+    monkeypatch.delenv("B200DP_DEFER_CLIP", raising=False)
+    acc = Accelerator(mixed_precision="fp16", kwargs_handlers=[GradScalerKwargs(init_scale=256.0, growth_interval=2)])
+    model, ref = mlp(13), mlp(13)
+    ddp = B200DataParallel(model, device_ids=[0], bucket_cap_mb=0.02)
+    opt = acc.prepare(torch.optim.AdamW(model.parameters(), lr=2e-3))
+    ref_opt = torch.optim.AdamW(ref.parameters(), lr=2e-3, foreach=True)
+    ref_scaler = torch.amp.GradScaler("cuda", init_scale=256.0, growth_interval=2)
+    rt = PartialState().runtime
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for step in range(6):
+        x = torch.randn(8, 64, device="cuda", generator=g)
+        boom = float("inf") if step == 2 else 1.0
+        with acc.autocast():
+            loss = ddp(x).float().square().mean() * boom
+        acc.backward(loss)
+        with torch.autocast("cuda", dtype=torch.float16):
+            ref_loss = ref(x).float().square().mean() * boom
+        ref_scaler.scale(ref_loss).backward()
+        if step % 2 == 0:  # clip on some steps (unscale+clip fused), plain step on the others
+            tn = acc.clip_grad_norm_(ddp.parameters(), 0.05)
+            ref_scaler.unscale_(ref_opt)
+            ref_tn = torch.nn.utils.clip_grad_norm_(ref.parameters(), 0.05)
+            if step != 2:
+                assert torch.allclose(tn, ref_tn, rtol=1e-4)
+        launches = rt.ctx.launches
+        opt.step()
+        assert opt._fused_plan is not None, "AdamW under a GradScaler must take the fused step"
+        assert not lazy_grad.has_pending()
+        ref_scaler.step(ref_opt)
+        ref_scaler.update()
+        assert opt.step_was_skipped == (step == 2)
+        assert acc.scaler.get_scale() == ref_scaler.get_scale()
+        opt.zero_grad()
+        ref_opt.zero_grad()
+        for p, q in zip(model.parameters(), ref.parameters()):
+            assert_tracks_torch(p, q, 2e-3, step, rtol=1e-4)
+    for p, q in zip(model.parameters(), ref.parameters()):
+        assert float(opt.optimizer.state[p]["step"]) == float(ref_opt.state[q]["step"]) == 5.0
+    rt.ctx.check_status()

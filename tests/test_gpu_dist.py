@@ -51,3 +51,35 @@ def test_bert_large_shaped_accumulation_and_clip_two_ranks():
     """BASELINE.json config 4: BERT-large-shaped seq-cls (1024/16/4096), bf16, accumulate(4) + fused clip + buffer broadcast."""
     out = run_distributed("dist_bert.py", 2, "--device", "cuda", env=ENV, timeout=1200)
     assert out.count("BERT_CHECK_OK") == 2, out[-3000:]
+
+
+# ---- CUDA legs of features whose host logic is pinned on gloo by tests/test_dist_cpu.py (round-1 backlog) ----
+SHORT = {"B200DP_TIMEOUT_MS": "30000"}  # a divergence fails in 30 s instead of hanging
+
+
+@pytest.mark.parametrize("find_unused", ["0", "1"])
+def test_join_uneven_inputs_cuda(find_unused):
+    """reference accelerator.py:1299-1380 `join_uneven_inputs` (pinned by test_distributed_data_loop.py:162-183): ranks
+    train 3+2r iterations, early finishers shadow every bucket reduction with zeros through the same kernels."""
+    out = run_distributed("dist_join.py", 2, "--device", "cuda", env=dict(SHORT, JOIN_FIND_UNUSED=find_unused), timeout=300)
+    assert out.count("JOIN_OK") == 2, out[-3000:]
+
+
+def test_unused_parameters_cuda():
+    """find_unused_parameters=True (dataclasses.py:181-195): the used-map allreduce runs over b200dp_push."""
+    out = run_distributed("dist_unused.py", 2, "--device", "cuda", env=SHORT, timeout=300)
+    assert out.count("UNUSED_OK") == 2, out[-3000:]
+
+
+def test_user_and_powersgd_hooks_cuda():
+    """PowerSGD / wrapped / user hooks through torch's plug point on CUDA ranks (dataclasses.py:200-237; tolerance of
+    test_ddp_comm_hook.py:57)."""
+    out = run_distributed("dist_comm_hook.py", 2, "--device", "cuda", env=dict(SHORT, B200DP_TEST_CUDA_HOOKS="1"), timeout=600)
+    assert out.count("COMM_HOOK_OK") == 2, out[-3000:]
+
+
+def test_three_ranks_two_shot_bit_exact():
+    """A non-power-of-two world never takes the NVLS kernel (its scale-after-sum differs from the oracle's pre-divide
+    in the last ulp): bit-exact vs the oracle at N=3."""
+    out = run_distributed("dist_allreduce_check.py", 3, env=ENV, timeout=600)
+    assert out.count("ALLREDUCE_CHECK_OK") == 3, out[-3000:]
