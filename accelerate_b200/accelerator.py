@@ -582,7 +582,8 @@ class Accelerator:
 
         rt = SymmRuntime.get()
         st = torch.cuda.current_stream(self.device).cuda_stream
-        lazy_grad.flush_all()  # an earlier pending multiplier belongs to these values
+        if lazy_grad.has_pending():  # an earlier pending multiplier belongs to these values
+            lazy_grad.flush_params({id(p) for p in params})
         by_dtype = {}
         for p in params:
             g = raw_grad(p)
@@ -611,7 +612,8 @@ class Accelerator:
                                    out.data_ptr() + 4, stream)  # fmt: skip
 
         if defer:
-            lazy_grad.defer(out, apply, owner=frozenset(g.data_ptr() for grads in by_dtype.values() for g in grads))
+            lazy_grad.defer(out, apply, owner=frozenset(g.data_ptr() for grads in by_dtype.values() for g in grads),
+                            param_ids=frozenset(id(p) for p in params))
         else:
             apply()
         return out[0]

@@ -58,13 +58,14 @@ def all_gather(t: torch.Tensor) -> torch.Tensor:
     if nbytes <= rt.push_max:  # latency path: one launch, one cross-GPU barrier
         rt.ctx.push(staging.seg, 0, t.data_ptr(), nbytes, native.U8, 1.0, out.data_ptr(), native.CH_PUSH, st)
         return out
+    # large path: ONE fused launch per staging-window-sized piece — CTA b stages its portion and pulls the same portion
+    # from every peer as soon as their CTA b has staged theirs (b200dp_gather); no separate pack, no round trip
     cap = _bulk_capacity(rt, staging)
     src, dst = t.data_ptr(), out.data_ptr()
     done = 0
     while done < nbytes:
         n = min(cap, nbytes - done)
-        rt.ctx.pack([src + done], [staging.ptr], [n], rt.use_bulk_pack, st)
-        rt.ctx.pull(staging.seg, 0, n, dst + done, nbytes, 0, world, native.CH_USER, 0, st)
+        rt.ctx.gather(staging.seg, 0, src + done, n, dst + done, nbytes, native.CH_USER, 0, st)
         done += n
     return out
 
@@ -95,24 +96,22 @@ def all_reduce(t: torch.Tensor, mean: bool = False) -> torch.Tensor:
     if nbytes <= rt.push_max:  # latency path: one launch, one cross-GPU barrier
         rt.ctx.push(staging.seg, 1, src.data_ptr(), nbytes, dt, divisor, out.data_ptr(), native.CH_PUSH, st)
         return out.view(t.shape)
-    cap_elems = _bulk_capacity(rt, staging) // es
+    cap_elems = _bulk_capacity(rt, staging) // 16 * 16 // es
     large = nbytes > ONESHOT_MAX_BYTES and src.dtype in fused_types
+    algo = native.ALGO_NVLS if (staging.multicast and world >= 4) else native.ALGO_TWOSHOT
     done = 0
     while done < numel:
         n = min(cap_elems, numel - done)
-        nb = n * es
-        rt.ctx.pack([src.data_ptr() + done * es], [staging.ptr], [nb], rt.use_bulk_pack, st)
-        if not large:
-            rt.ctx.allreduce_oneshot(staging.seg, 0, n, dt, divisor, out.data_ptr() + done * es, native.CH_USER, 0, st)
+        if large:
+            # ONE fused launch (b200dp_reduce): CTA b stages its portion, the owners reduce their share of it over all
+            # ranks' staged copies (two-shot by peer loads, or NVLS in the switch) and write the result into every
+            # rank's staging, CTA b copies its portion out — dividing on the way for "mean", like the reference's `/= N`
+            rt.ctx.reduce(staging.seg, 0, src.data_ptr() + done * es, n, dt, divisor, out.data_ptr() + done * es, algo,
+                          native.CH_USER, 0, st)  # fmt: skip
         else:
-            # two-shot / NVLS in place on the staging copy, then one copy out
-            padded = (nb + 15) // 16 * 16 // es
-            rt.ctx.allreduce_bucket(staging.seg, 0, padded, dt, 1.0, -1, 0, native.ALGO_AUTO if staging.multicast
-                                    else native.ALGO_TWOSHOT, native.CH_USER, 0, native.NO_STREAM, st)  # fmt: skip
-            rt.ctx.pack([staging.ptr], [out.data_ptr() + done * es], [nb], rt.use_bulk_pack, st)
+            rt.ctx.pack([src.data_ptr() + done * es], [staging.ptr], [n * es], rt.bulk_for(n * es), st)
+            rt.ctx.allreduce_oneshot(staging.seg, 0, n, dt, divisor, out.data_ptr() + done * es, native.CH_USER, 0, st)
         done += n
-    if mean and large:
-        out /= world  # same op the reference applies (`/= N`) on the large-tensor path
     return out.view(t.shape)
 
 
@@ -130,7 +129,7 @@ def broadcast_(t: torch.Tensor, src: int = 0) -> torch.Tensor:
         while done < nbytes:
             n = min(cap, nbytes - done)
             if rt.rank == src:
-                rt.ctx.pack([work.data_ptr() + done], [staging.ptr], [n], rt.use_bulk_pack, st)
+                rt.ctx.pack([work.data_ptr() + done], [staging.ptr], [n], rt.bulk_for(n), st)
             rt.ctx.pull(staging.seg, 0, n, work.data_ptr() + done, 0, src, 1, native.CH_USER, 0, st)
             done += n
     if work is not t:

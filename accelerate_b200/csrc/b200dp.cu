@@ -1033,10 +1033,12 @@ static BulkCfg bulk_cfg() {
       return v < lo ? lo : (v > hi ? hi : v);
     };
     BulkCfg c;
+    // defaults from the single-GPU sweep (profiles/r02_pack_sweep_n1.jsonl): 4 issuing warps x 2 stages x 8 KB, 2 CTAs
+    // per SM = 6.43 TB/s on 1 GB (98 % of the measured copy peak); 64 KB of shared memory per CTA
     c.warps = geti("B200DP_BULK_WARPS", 4, 1, kBulkMaxWarps);
-    c.stages = geti("B200DP_BULK_STAGES", 3, 2, kBulkMaxStages);
-    c.stage_bytes = geti("B200DP_BULK_STAGE_KB", 16, 1, 64) * 1024;
-    c.ctas_per_sm = geti("B200DP_BULK_CTAS_PER_SM", 1, 1, 4);
+    c.stages = geti("B200DP_BULK_STAGES", 2, 2, kBulkMaxStages);
+    c.stage_bytes = geti("B200DP_BULK_STAGE_KB", 8, 1, 64) * 1024;
+    c.ctas_per_sm = geti("B200DP_BULK_CTAS_PER_SM", 2, 1, 4);
     while (size_t(c.warps) * c.stages * c.stage_bytes > size_t(220) * 1024 / c.ctas_per_sm && c.stages > 2) --c.stages;
     while (size_t(c.warps) * c.stages * c.stage_bytes > size_t(220) * 1024 / c.ctas_per_sm && c.warps > 1) --c.warps;
     return c;
@@ -1127,6 +1129,101 @@ extern "C" int b200dp_pull(b200dp_ctx* c, int seg, size_t byte_off, size_t nbyte
   a.nranks = nranks;
   const int grid = clamp_blocks(c, (nbytes / 16 + 1) * size_t(nranks), size_t(kThreads) * 4, max_blocks);
   pull_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);
+  KERNEL_OK(c);
+  return B200DP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2c / K1c: fused large-message gather / reduce (stage + exchange in one launch)
+// ------------------------------------------------------------------------------------------------
+static int env_blocks(const char* name, int dflt) {
+  const char* e = getenv(name);
+  int v = e ? atoi(e) : 0;
+  return v > 0 ? v : dflt;
+}
+
+extern "C" int b200dp_gather(b200dp_ctx* c, int seg, size_t byte_off, const void* src, size_t nbytes, void* dst,
+                             size_t dst_stride, int channel, int max_blocks, void* stream) {
+  Segment* s;
+  int rc = get_seg(c, seg, &s);
+  if (rc) return rc;
+  if ((rc = all_mapped(c, *s))) return rc;
+  if (byte_off & 15) return fail(B200DP_EINVAL, "staging offset must be 16-byte aligned");
+  if (byte_off + round_up(nbytes, 16) > s->bytes) return fail(B200DP_EINVAL, "staging range exceeds segment");
+  if (nbytes == 0) return B200DP_OK;
+  if (!src || !dst) return fail(B200DP_EINVAL, "null src/dst");
+  DeviceGuard g(c->device);
+  GatherArgs a;
+  if ((rc = make_barrier(c, channel, &a.bar))) return rc;
+  fill_peers(c, *s, &a.bufs);
+  a.byte_off = byte_off;
+  a.nbytes = nbytes;
+  a.src = reinterpret_cast<const char*>(src);
+  a.dst = reinterpret_cast<char*>(dst);
+  a.dst_stride = dst_stride;
+  static const int dflt = env_blocks("B200DP_GATHER_BLOCKS", 32);
+  const int grid = clamp_blocks(c, (nbytes + 15) / 16, size_t(kThreads) * 4, max_blocks > 0 ? max_blocks : dflt);
+  gather_fused_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);
+  KERNEL_OK(c);
+  return B200DP_OK;
+}
+
+template <typename T>
+static void launch_reduce(const ReduceArgs& a, int world, bool nvls, int grid, cudaStream_t st) {
+  if (nvls) {
+    reduce_fused_kernel<T, 0, true><<<grid, kThreads, 0, st>>>(a);
+    return;
+  }
+  switch (world) {
+    case 2: reduce_fused_kernel<T, 2, false><<<grid, kThreads, 0, st>>>(a); break;
+    case 4: reduce_fused_kernel<T, 4, false><<<grid, kThreads, 0, st>>>(a); break;
+    case 8: reduce_fused_kernel<T, 8, false><<<grid, kThreads, 0, st>>>(a); break;
+    default: reduce_fused_kernel<T, 0, false><<<grid, kThreads, 0, st>>>(a); break;
+  }
+}
+
+extern "C" int b200dp_reduce(b200dp_ctx* c, int seg, size_t byte_off, const void* src, size_t count, int dtype,
+                             double divisor, void* dst, int algo, int channel, int max_blocks, void* stream) {
+  Segment* s;
+  int rc = get_seg(c, seg, &s);
+  if (rc) return rc;
+  if ((rc = all_mapped(c, *s))) return rc;
+  if (dtype != B200DP_F32 && dtype != B200DP_BF16 && dtype != B200DP_F16)
+    return fail(B200DP_EINVAL, "b200dp_reduce supports f32/bf16/f16, got dtype %d", dtype);
+  const size_t es = dtype_size(dtype);
+  if (byte_off & 15) return fail(B200DP_EINVAL, "staging offset must be 16-byte aligned");
+  if (byte_off + round_up(count * es, 16) > s->bytes) return fail(B200DP_EINVAL, "staging range exceeds segment");
+  if (count == 0) return B200DP_OK;
+  if (!src || !dst) return fail(B200DP_EINVAL, "null src/dst");
+  if ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) % es)
+    return fail(B200DP_EINVAL, "src/dst not aligned to the element size");
+  bool nvls = false;
+  if (algo == B200DP_ALGO_NVLS) {
+    if (!s->mc_bound) return fail(B200DP_ESTATE, "NVLS requested but segment %d has no multicast binding", seg);
+    nvls = true;
+  } else if (algo == B200DP_ALGO_AUTO) {
+    nvls = s->mc_bound && c->world >= 4;
+  } else if (algo != B200DP_ALGO_TWOSHOT) {
+    return fail(B200DP_EINVAL, "bad algo %d for b200dp_reduce", algo);
+  }
+  DeviceGuard g(c->device);
+  ReduceArgs a;
+  if ((rc = make_barrier(c, channel, &a.bar))) return rc;
+  fill_peers(c, *s, &a.bufs);
+  a.mc = reinterpret_cast<char*>(s->mc_ptr);
+  a.byte_off = byte_off;
+  a.count = count;
+  a.src = src;
+  a.dst = dst;
+  a.divisor = float(divisor);
+  static const int dflt = env_blocks("B200DP_REDUCE_FUSED_BLOCKS", 32);
+  const int grid = clamp_blocks(c, (count * es + 15) / 16, size_t(kThreads) * 4, max_blocks > 0 ? max_blocks : dflt);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case B200DP_F32: launch_reduce<float>(a, c->world, nvls, grid, st); break;
+    case B200DP_BF16: launch_reduce<__nv_bfloat16>(a, c->world, nvls, grid, st); break;
+    default: launch_reduce<__half>(a, c->world, nvls, grid, st); break;
+  }
   KERNEL_OK(c);
   return B200DP_OK;
 }

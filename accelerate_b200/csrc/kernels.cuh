@@ -420,6 +420,199 @@ __global__ void __launch_bounds__(kThreads, 1) pull_kernel(const PullArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// K2c / K1c: fused large-message collectives for tensors that live in ordinary (not peer-mapped) torch memory.
+// ONE launch each: CTA b stages ITS portion of the local input into the symmetric staging segment, meets CTA b of
+// every other rank at a flag barrier, and then moves exactly that portion over NVLink.  Because the hand-off is per
+// CTA, portions pipeline against each other (some CTAs still stage while others already pull) and there is no
+// separate pack launch, no grid-wide barrier and no second pass over the output.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void copy_any(char* dst, const char* src, size_t nbytes, size_t tid, size_t nthreads) {
+  const uintptr_t al = reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src);
+  if ((al & 15) == 0) {
+    const size_t nvec = nbytes >> 4;
+    constexpr int U = 4;
+    for (size_t i = tid; i < nvec; i += U * nthreads) {
+      uint4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const size_t j = i + u * nthreads;
+        if (j < nvec) v[u] = ld_stream16(src + j * 16);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const size_t j = i + u * nthreads;
+        if (j < nvec) st_stream16(dst + j * 16, v[u]);
+      }
+    }
+    for (size_t i = (nvec << 4) + tid; i < nbytes; i += nthreads) dst[i] = src[i];
+  } else if ((al & 3) == 0) {
+    const size_t nw = nbytes >> 2;
+    for (size_t i = tid; i < nw; i += nthreads)
+      reinterpret_cast<uint32_t*>(dst)[i] = reinterpret_cast<const uint32_t*>(src)[i];
+    for (size_t i = (nw << 2) + tid; i < nbytes; i += nthreads) dst[i] = src[i];
+  } else {
+    for (size_t i = tid; i < nbytes; i += nthreads) dst[i] = src[i];
+  }
+}
+
+struct GatherArgs {
+  BarrierCtx bar;
+  Peers bufs;          // staging segment bases
+  size_t byte_off;     // staging window (16-byte aligned)
+  size_t nbytes;       // bytes per rank in this call
+  const char* src;     // local input
+  char* dst;           // local output: rank r's block at dst + r * dst_stride
+  size_t dst_stride;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) gather_fused_kernel(const GatherArgs a) {
+  const BarrierCtx& b = a.bar;
+  const uint32_t base = barrier_seq_begin(b);
+  const size_t nvec = (a.nbytes + 15) >> 4;
+  const size_t per = (nvec + gridDim.x - 1) / gridDim.x;
+  size_t lo = size_t(blockIdx.x) * per * 16, hi = lo + per * 16;
+  if (lo > a.nbytes) lo = a.nbytes;
+  if (hi > a.nbytes) hi = a.nbytes;
+  const size_t n = hi - lo;
+  char* mine = reinterpret_cast<char*>(a.bufs.p[b.rank]) + a.byte_off + lo;
+  copy_any(mine, a.src + lo, n, threadIdx.x, blockDim.x);
+  cross_rank_barrier(b, base + 1);  // CTA b of every rank has staged portion b
+  // own block straight from the staged copy, then the peers, starting with the next rank (N readers, N sources)
+  for (int k = 0; k < b.world; ++k) {
+    const int r = (b.rank + k) % b.world;
+    copy_span(a.dst + size_t(r) * a.dst_stride + lo, reinterpret_cast<const char*>(a.bufs.p[r]) + a.byte_off + lo, n,
+              threadIdx.x, blockDim.x);
+  }
+  // nobody may restage (next call) while a peer still reads this window
+  cross_rank_barrier(b, base + 2);
+  barrier_seq_end(b, base, 2);
+}
+
+struct ReduceArgs {
+  BarrierCtx bar;
+  Peers bufs;        // staging segment bases
+  char* mc;          // multicast VA of the staging segment (NVLS) or nullptr
+  size_t byte_off;   // staging window (16-byte aligned)
+  size_t count;      // elements
+  const void* src;   // local input
+  void* dst;         // local output
+  float divisor;     // 1 = plain sum; else out = T(float(T(sum)) / divisor)  (the reference's `t /= N` in t's dtype)
+};
+
+// T in {float, bf16, half}.  W > 0: ranks known at compile time; W == 0: any world size.
+template <typename T, int W, bool NVLS>
+__global__ void __launch_bounds__(kThreads, 1) reduce_fused_kernel(const ReduceArgs a) {
+  constexpr int N = Vec16<T>::N;
+  const BarrierCtx& b = a.bar;
+  const uint32_t base = barrier_seq_begin(b);
+  const int world = b.world;
+  const size_t nbytes = a.count * sizeof(T);
+  const size_t nvec = (nbytes + 15) >> 4;
+  const size_t per = (nvec + gridDim.x - 1) / gridDim.x;
+  size_t vlo = size_t(blockIdx.x) * per, vhi = vlo + per;
+  if (vlo > nvec) vlo = nvec;
+  if (vhi > nvec) vhi = nvec;
+  size_t blo = vlo * 16, bhi = vhi * 16;
+  if (bhi > nbytes) bhi = nbytes;
+  if (blo > nbytes) blo = nbytes;
+  char* mine = reinterpret_cast<char*>(a.bufs.p[b.rank]) + a.byte_off;
+  // A: stage this CTA's portion (the bytes past `count` in the last vector keep whatever they held: never copied out)
+  copy_any(mine + blo, reinterpret_cast<const char*>(a.src) + blo, bhi - blo, threadIdx.x, blockDim.x);
+  cross_rank_barrier(b, base + 1);
+  // B: rank r owns the r-th 1/N of the portion: reduce it over all ranks' staged copies (rank order, fp32 accumulate,
+  // one rounding to T), store the result into every rank's staging
+  const size_t sub = (vhi - vlo + world - 1) / world;
+  size_t slo = vlo + size_t(b.rank) * sub, shi = slo + sub;
+  if (slo > vhi) slo = vhi;
+  if (shi > vhi) shi = vhi;
+  if constexpr (NVLS) {
+    char* mcb = a.mc + a.byte_off;
+    constexpr int U = 4;
+    for (size_t i = slo + threadIdx.x; i < shi; i += size_t(U) * blockDim.x) {
+      uint4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const size_t j = i + size_t(u) * blockDim.x;
+        if (j < shi) v[u] = MultimemOps<T>::ld_reduce(mcb + j * 16);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const size_t j = i + size_t(u) * blockDim.x;
+        if (j < shi) multimem_st16(mcb + j * 16, v[u]);
+      }
+    }
+  } else {
+    constexpr int U = (W == 0 || W >= 5) ? 2 : 4;
+    for (size_t i = slo + threadIdx.x; i < shi; i += size_t(U) * blockDim.x) {
+      float acc[U][N];
+      bool ok[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const size_t j = i + size_t(u) * blockDim.x;
+        ok[u] = j < shi;
+        if (!ok[u]) continue;
+        if constexpr (W > 0) {
+          uint4 v[W];
+#pragma unroll
+          for (int r = 0; r < W; ++r) v[r] = ld_stream16(reinterpret_cast<const char*>(a.bufs.p[r]) + a.byte_off + j * 16);
+          Vec16<T>::unpack(v[0], acc[u]);
+#pragma unroll
+          for (int r = 1; r < W; ++r) {
+            float x[N];
+            Vec16<T>::unpack(v[r], x);
+#pragma unroll
+            for (int k = 0; k < N; ++k) acc[u][k] = __fadd_rn(acc[u][k], x[k]);
+          }
+        } else {
+          Vec16<T>::unpack(ld_stream16(reinterpret_cast<const char*>(a.bufs.p[0]) + a.byte_off + j * 16), acc[u]);
+          for (int r = 1; r < world; ++r) {
+            float x[N];
+            Vec16<T>::unpack(ld_stream16(reinterpret_cast<const char*>(a.bufs.p[r]) + a.byte_off + j * 16), x);
+#pragma unroll
+            for (int k = 0; k < N; ++k) acc[u][k] = __fadd_rn(acc[u][k], x[k]);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (!ok[u]) continue;
+        const size_t j = i + size_t(u) * blockDim.x;
+        const uint4 o = Vec16<T>::pack(acc[u]);
+        for (int r = 0; r < world; ++r) st_stream16(reinterpret_cast<char*>(a.bufs.p[r]) + a.byte_off + j * 16, o);
+      }
+    }
+  }
+  cross_rank_barrier(b, base + 2);  // every owner's results for portion b have landed in my staging
+  // C: staging -> output, dividing on the way if asked (peers only ever read my staging before barrier 2 and write it
+  // between the barriers, so the next call may restage at once: no closing barrier)
+  const char* st = mine;
+  char* out = reinterpret_cast<char*>(a.dst);
+  if (a.divisor == 1.0f) {
+    copy_span(out + blo, st + blo, bhi - blo, threadIdx.x, blockDim.x);
+  } else {
+    const size_t elo = blo / sizeof(T), ehi = bhi / sizeof(T);
+    const T* sp = reinterpret_cast<const T*>(st);
+    T* op = reinterpret_cast<T*>(out);
+    if ((reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+      for (size_t j = vlo + threadIdx.x; j < vhi; j += blockDim.x) {
+        if ((j + 1) * N <= a.count) {
+          float f[N];
+          Vec16<T>::unpack(ld_stream16(st + j * 16), f);
+#pragma unroll
+          for (int k = 0; k < N; ++k) f[k] = __fdiv_rn(f[k], a.divisor);
+          *reinterpret_cast<uint4*>(out + j * 16) = Vec16<T>::pack(f);
+        } else {
+          for (size_t e = j * N; e < a.count; ++e) op[e] = from_float<T>(__fdiv_rn(to_float<T>(sp[e]), a.divisor));
+        }
+      }
+    } else {
+      for (size_t e = elo + threadIdx.x; e < ehi; e += blockDim.x) op[e] = from_float<T>(__fdiv_rn(to_float<T>(sp[e]), a.divisor));
+    }
+  }
+  barrier_seq_end(b, base, 2);
+}
+
+// ------------------------------------------------------------------------------------------------
 // K2b: latency path for small messages: ONE launch, ONE barrier.  Every rank pushes its data into a
 // fixed window of every peer's staging segment (posted NVLink stores), then reads all N windows
 // locally and either concatenates (gather) or sums in rank order (reduce).  Windows are private to a

@@ -34,6 +34,7 @@ raw_grad = _DESC.__get__  # raw_grad(p): p.grad without observing it
 raw_set_grad = _DESC.__set__
 
 _pending: list = []  # PendingScale objects neither consumed nor applied yet
+assign_epoch = 0  # bumped by every Python-level assignment to a Parameter's .grad (once the observer is installed)
 _lock = threading.RLock()
 _installed = False
 
@@ -46,10 +47,11 @@ class PendingScale:
     """``out`` = device tensor [total_norm, multiplier, found_inf]; ``apply()`` multiplies the gradients it was
     computed for by ``out[1]`` in place (stream-ordered, exits at once on the device when the multiplier is 1)."""
 
-    __slots__ = ("out", "_apply", "owner", "done")
+    __slots__ = ("out", "_apply", "owner", "param_ids", "done")
 
-    def __init__(self, out: torch.Tensor, apply, owner=None):
+    def __init__(self, out: torch.Tensor, apply, owner=None, param_ids=None):
         self.out, self._apply, self.owner, self.done = out, apply, owner, False
+        self.param_ids = param_ids  # ids of the parameters whose gradients wait for the multiplier (None: any)
 
     @property
     def mult_ptr(self) -> int:
@@ -82,9 +84,9 @@ class PendingScale:
                 _pending.remove(self)
 
 
-def defer(out: torch.Tensor, apply, owner=None) -> PendingScale:
+def defer(out: torch.Tensor, apply, owner=None, param_ids=None) -> PendingScale:
     install()
-    p = PendingScale(out, apply, owner)
+    p = PendingScale(out, apply, owner, param_ids)
     with _lock:
         _pending.append(p)
     return p
@@ -102,7 +104,7 @@ def take_for(owner):
 
 
 def flush_all():
-    """Apply every pending multiplier (called on the first observation of a ``Parameter.grad``)."""
+    """Apply every pending multiplier."""
     while _pending:
         with _lock:
             if not _pending:
@@ -111,24 +113,45 @@ def flush_all():
         p.apply()
 
 
+def flush_for(param):
+    """Apply the pending multipliers that cover ``param`` (called on the first observation of its ``.grad``)."""
+    pid = id(param)
+    for p in list(_pending):
+        if p.param_ids is None or pid in p.param_ids:
+            p.apply()
+
+
+def flush_params(param_ids):
+    """Apply the pending multipliers that cover any of ``param_ids``."""
+    for p in list(_pending):
+        if p.param_ids is None or not p.param_ids.isdisjoint(param_ids):
+            p.apply()
+
+
 def has_pending() -> bool:
     return bool(_pending)
 
 
 def _get(self):
     if _pending:
-        flush_all()
+        flush_for(self)
     return raw_grad(self)
 
 
 def _set(self, value):
+    global assign_epoch
     if _pending:
-        flush_all()
+        flush_for(self)
+    assign_epoch += 1
     raw_set_grad(self, value)
 
 
 def _del(self):
     raise RuntimeError("cannot delete a tensor's .grad; set it to None")
+
+
+def installed() -> bool:
+    return _installed
 
 
 def install():

@@ -45,7 +45,7 @@ EXPORTS = [
     "b200dp_set_control", "b200dp_fdx_open", "b200dp_fdx_send", "b200dp_fdx_recv", "b200dp_fdx_close",
     "b200dp_stream_wait", "b200dp_fence", "b200dp_allreduce_bucket", "b200dp_allreduce_oneshot", "b200dp_finalize_norm",
     "b200dp_scale_flat", "b200dp_clamp_flat", "b200dp_cast", "b200dp_multi_stats", "b200dp_multi_scale", "b200dp_multi_adam", "b200dp_pack",
-    "b200dp_pull", "b200dp_push_max_bytes", "b200dp_push_area_bytes", "b200dp_push", "b200dp_exchange_small",
+    "b200dp_pull", "b200dp_gather", "b200dp_reduce", "b200dp_push_max_bytes", "b200dp_push_area_bytes", "b200dp_push", "b200dp_exchange_small",
     "b200dp_pad_copy",
 ]  # fmt: skip
 
@@ -159,6 +159,8 @@ def load():
                                   c_double, c_double, c_double, c_double, c_double, vp, vp, vp],
             "b200dp_pack": [vp, POINTER(vp), POINTER(vp), POINTER(sz), i, i, vp],
             "b200dp_pull": [vp, i, sz, sz, vp, sz, i, i, i, i, vp],
+            "b200dp_gather": [vp, i, sz, vp, sz, vp, sz, i, i, vp],
+            "b200dp_reduce": [vp, i, sz, vp, sz, i, c_double, vp, i, i, i, vp],
             "b200dp_push": [vp, i, i, vp, sz, i, c_double, vp, i, vp],
             "b200dp_exchange_small": [vp, vp, i, vp, vp],
             "b200dp_pad_copy": [vp, vp, vp, sz, sz, sz, sz, i, c_uint64, i, vp],
@@ -359,10 +361,12 @@ class Context:
         )  # fmt: skip
 
     def pack(self, srcs, dsts, nbytes, use_bulk, stream):
+        """``srcs`` / ``dsts`` / ``nbytes``: Python sequences, or ctypes arrays built once (the reducer caches the
+        destination pointers and sizes of every bucket: only the sources change from step to step)."""
         n = len(srcs)
-        sa = (c_void_p * n)(*srcs)
-        da = (c_void_p * n)(*dsts)
-        ba = (c_size_t * n)(*nbytes)
+        sa = srcs if isinstance(srcs, ctypes.Array) else (c_void_p * n)(*srcs)
+        da = dsts if isinstance(dsts, ctypes.Array) else (c_void_p * n)(*dsts)
+        ba = nbytes if isinstance(nbytes, ctypes.Array) else (c_size_t * n)(*nbytes)
         _check(self.lib, self.lib.b200dp_pack(self.h, sa, da, ba, n, int(use_bulk), stream), "b200dp_pack")
 
     def pull(self, seg, byte_off, nbytes, dst, dst_stride, first, nranks, channel, max_blocks, stream):
@@ -371,6 +375,14 @@ class Context:
             self.lib.b200dp_pull(self.h, seg, byte_off, nbytes, dst, dst_stride, first, nranks, channel, max_blocks, stream),
             "b200dp_pull",
         )
+
+    def gather(self, seg, byte_off, src, nbytes, dst, dst_stride, channel, max_blocks, stream):
+        _check(self.lib, self.lib.b200dp_gather(self.h, seg, byte_off, src, nbytes, dst, dst_stride, channel, max_blocks, stream),
+               "b200dp_gather")  # fmt: skip
+
+    def reduce(self, seg, byte_off, src, count, dtype, divisor, dst, algo, channel, max_blocks, stream):
+        _check(self.lib, self.lib.b200dp_reduce(self.h, seg, byte_off, src, count, dtype, float(divisor), dst, algo, channel,
+                                                max_blocks, stream), "b200dp_reduce")  # fmt: skip
 
     def push(self, seg, mode, src, nbytes, dtype, divisor, dst, channel, stream):
         _check(self.lib, self.lib.b200dp_push(self.h, seg, mode, src, nbytes, dtype, float(divisor), dst, channel, stream), "b200dp_push")

@@ -79,14 +79,18 @@ class FusedAdamPlan:
         self.m_flat = torch.zeros(total, dtype=torch.float32, device=device)
         self.v_flat = torch.zeros(total, dtype=torch.float32, device=device)
         self.tables = []
-        self.views = {}  # id(param) -> (exp_avg view, exp_avg_sq view) installed in optimizer.state
+        self.views = {}  # id(param) -> (exp_avg view, exp_avg_sq view, step view) installed in optimizer.state
+        self.step_flats = []  # one CPU float32 vector per parameter group: state[p]["step"] are 0-dim views of it, so
+        #                       the per-step `step += 1` is ONE host op instead of a foreach over ~300 scalars
         self.signature = self._signature(optimizer)
         for pg in optimizer.param_groups:
             params = [p for p in pg["params"] if p.requires_grad]
             ptrs, numels, offs, gptrs = [], [], [], []
-            for p in params:
+            step_flat = torch.zeros(len(params), dtype=torch.float32)
+            self.step_flats.append(step_flat)
+            for k, p in enumerate(params):
                 off, n = where[id(p)]
-                self.views[id(p)] = (self.m_flat[off : off + n].view(p.shape), self.v_flat[off : off + n].view(p.shape))
+                self.views[id(p)] = (self.m_flat[off : off + n].view(p.shape), self.v_flat[off : off + n].view(p.shape), step_flat[k])
                 ptrs.append(p.data_ptr())
                 numels.append(n)
                 offs.append(off)
@@ -102,17 +106,20 @@ class FusedAdamPlan:
     def _adopt_state(self):
         """Make ``optimizer.state[p]['exp_avg'/'exp_avg_sq']`` the views of the flat moment buffers.  Values that
         are already there (a resumed run, or ``load_state_dict`` replacing the tensors) are copied in first."""
+        state, views = self.optimizer.state, self.views
         for params, _ in self.tables:
             for p in params:
-                st = self.optimizer.state[p]
-                m_view, v_view = self.views[id(p)]
+                st = state[p]
+                m_view, v_view, s_view = views[id(p)]
                 if st.get("exp_avg") is not m_view:
                     if "exp_avg" in st:
                         m_view.copy_(st["exp_avg"])
                         v_view.copy_(st["exp_avg_sq"])
                     st["exp_avg"], st["exp_avg_sq"] = m_view, v_view
-                if "step" not in st:
-                    st["step"] = torch.tensor(0.0, dtype=torch.float32)
+                if st.get("step") is not s_view:
+                    if "step" in st:
+                        s_view.fill_(float(st["step"]))
+                    st["step"] = s_view
 
     @staticmethod
     def try_build(optimizer):
@@ -177,19 +184,18 @@ class FusedAdamPlan:
         elif lazy_grad.has_pending():
             pending = lazy_grad.take_for(frozenset(ptr for grads in grads_per_group for ptr in grads))
             pending = pending.out if pending is not None else None
-        if lazy_grad.has_pending():
-            lazy_grad.flush_all()  # multipliers of other gradient sets: not ours to fold in
+        if lazy_grad.has_pending():  # a multiplier computed for a different selection of these gradients: materialise it
+            lazy_grad.flush_params({id(p) for params, _ in self.tables for p in params})
         mult_ptr = pending.data_ptr() + 4 if pending is not None else None
         # without a GradScaler torch applies the update even to non-finite gradients: keep that (found_ptr None)
         found_ptr = found_inf.data_ptr() if found_inf is not None else None
         self.last_steps = []
-        for pg, (params, table), grads in zip(self.optimizer.param_groups, self.tables, grads_per_group):
+        for pg, (params, table), grads, step_flat in zip(self.optimizer.param_groups, self.tables, grads_per_group, self.step_flats):
             if not params:
                 continue
-            steps = [self.optimizer.state[p]["step"] for p in params]
-            torch._foreach_add_(steps, 1)
-            self.last_steps.extend(steps)
-            t = float(steps[0])
+            step_flat.add_(1.0)
+            self.last_steps.append(step_flat)
+            t = float(step_flat[0])
             lr, (beta1, beta2), eps, wd = float(pg["lr"]), pg["betas"], float(pg["eps"]), float(pg["weight_decay"])
             decoupled = pg.get("decoupled_weight_decay", self.decoupled_default)
             decay_mul = (1 - lr * wd) if (decoupled and wd != 0) else 1.0

@@ -102,7 +102,7 @@ def compute_bucket_assignment(sizes_bytes, keys, first_cap: int, cap: int):
 class GradBucket:
     __slots__ = (
         "index", "group", "elem_off", "count", "params", "offsets", "numels", "views", "ptrs", "nbytes",
-        "pending", "seen", "staged", "slot", "flat",
+        "pending", "seen", "staged", "slot", "flat", "c_ptrs", "c_nbytes",
     )  # fmt: skip
 
     def __init__(self, index, group):
@@ -114,6 +114,7 @@ class GradBucket:
         self.staged = []
         self.slot = -1
         self.flat = None
+        self.c_ptrs = self.c_nbytes = None  # ctypes arrays of ptrs / nbytes, built once (CUDA)
 
     def reset(self):
         self.pending = len(self.params)
@@ -190,6 +191,7 @@ class GradReducer:
         self._wire_dirty = False
         self._pending_mult = None  # lazy_grad.PendingScale of a deferred clip
         self._stats_versions = []
+        self._views_epoch = -1
         self._closed = False
         self._locally_undefined = []  # (bucket, i) whose gradient was None when an unused parameter was filled in
         self._shadowing = False  # inside shadow_backward (a joined rank standing in for a backward it does not run)
@@ -200,6 +202,8 @@ class GradReducer:
             from .runtime import SymmRuntime, native_dtype
 
             self.rt = SymmRuntime.get()  # raises if the native runtime is not up: no fallback
+            if lazy_grad.enabled():
+                lazy_grad.install()  # observe Python-level .grad accesses from the start (deferred clip, epoch fast paths)
             self._native_dtype = native_dtype
             self.comm_stream = self.rt.ctx.comm_stream
             # CTAs per bucket kernel (0 = pick by algorithm).  Measured on 8xB200 (profiles/r01_sweep_n8_u4.json,
@@ -262,9 +266,13 @@ class GradReducer:
                 b.views.append(v)
                 b.ptrs.append(v.data_ptr())
         if self.is_cuda:
+            import ctypes
+
             self.slot_base = self.rt.reserve_slots(len(self.buckets))
             for b in self.buckets:
                 b.slot = self.slot_base + b.index
+                b.c_ptrs = (ctypes.c_void_p * len(b.ptrs))(*b.ptrs)
+                b.c_nbytes = (ctypes.c_size_t * len(b.nbytes))(*b.nbytes)
         self._managed_ids = frozenset(id(p) for p in params)
         self._param_index = {id(p): k for k, p in enumerate(params)}
         self._hooks = []
@@ -318,19 +326,22 @@ class GradReducer:
             comm = cs if _SAME_STREAM else self.comm_stream
             if b.staged:
                 srcs = [g.data_ptr() for _, g in b.staged]
-                dsts = [b.ptrs[i] for i, _ in b.staged]
-                sizes = [b.nbytes[i] for i, _ in b.staged]
+                if len(b.staged) == len(b.ptrs) and all(i == k for k, (i, _) in enumerate(b.staged)):
+                    dsts, sizes = b.c_ptrs, b.c_nbytes  # the usual case: every gradient of the bucket is fresh, in order
+                else:
+                    dsts = [b.ptrs[i] for i, _ in b.staged]
+                    sizes = [b.nbytes[i] for i, _ in b.staged]
                 if _PACK_ON_COMM and comm != cs and self.user_hook is None:
                     # adopt the gradients on the SIDE stream: the pack overlaps with the rest of backward instead
                     # of sitting on the compute stream.  The source tensors must then outlive the pack, so they
                     # are parked until the end-of-backward join (after which the compute stream is ordered behind
                     # the side stream and the allocator may hand the memory out again).
                     ctx.stream_wait(comm, cs)
-                    ctx.pack(srcs, dsts, sizes, self.rt.use_bulk_pack, comm)
+                    ctx.pack(srcs, dsts, sizes, self.rt.bulk_for(b.count * b.group.elem_size), comm)
                     self._graveyard.extend(g for _, g in b.staged)
                     pack_stream = comm
                 else:
-                    ctx.pack(srcs, dsts, sizes, self.rt.use_bulk_pack, cs)
+                    ctx.pack(srcs, dsts, sizes, self.rt.bulk_for(b.count * b.group.elem_size), cs)
                     pack_stream = cs
                 if _DEBUG:
                     print(f"[b200dp r{self.rank}] bucket {b.index}: pack {len(srcs)} spans on stream {pack_stream:#x}: "
@@ -512,6 +523,9 @@ class GradReducer:
                 # the native kernels do not touch torch's version counters; anything that writes a gradient through
                 # torch afterwards (p.grad.mul_(), a second backward accumulating into the views) does
                 self._stats_versions = [g.flat._version for g in self.groups.values()]
+                # every gradient is now its fusion-buffer view unless a parameter stayed undefined; until somebody assigns a
+                # .grad from Python (observed through lazy_grad's property) the per-parameter pointer walk can be skipped
+                self._views_epoch = lazy_grad.assign_epoch if not self._locally_undefined and not self.find_unused_parameters else -1
             if self.find_unused_parameters:
                 self._restore_globally_unused()
             self.num_reductions += 1
@@ -615,6 +629,8 @@ class GradReducer:
 
     def grads_in_buffer(self) -> bool:
         """Every managed parameter's ``.grad`` is (still) its view into the fusion buffer."""
+        if self._views_epoch == lazy_grad.assign_epoch and lazy_grad.installed():
+            return True
         for b in self.buckets:
             for p, ptr in zip(b.params, b.ptrs):
                 g = raw_grad(p)
@@ -638,6 +654,8 @@ class GradReducer:
     def manages(self, parameters) -> bool:
         """True iff ``parameters`` (those with grads) are exactly this reducer's parameters and their
         gradients live in its buffers — the precondition for using the fused statistics."""
+        if self._views_epoch == lazy_grad.assign_epoch and lazy_grad.installed():
+            return {id(p) for p in parameters} == self._managed_ids  # all gradients known to be the buffer's views
         ids = {id(p) for p in parameters if raw_grad(p) is not None}
         return ids == self._managed_ids and self.grads_in_buffer()
 
@@ -668,7 +686,7 @@ class GradReducer:
         if defer:
             # fused optimizer consumption: the multiplier stays pending; the fused Adam kernel
             # applies it on the fly, anything else that looks at a gradient first triggers the pass (lazy_grad.py)
-            self._pending_mult = lazy_grad.defer(out, lambda: self._apply_multiplier(out), owner=self)
+            self._pending_mult = lazy_grad.defer(out, lambda: self._apply_multiplier(out), owner=self, param_ids=self._managed_ids)
         else:
             self._apply_multiplier(out)
         if scale is not None:
@@ -678,12 +696,28 @@ class GradReducer:
         return out
 
     def _apply_multiplier(self, out: torch.Tensor):
-        """One multiply pass over the fusion buffer by ``out[1]`` (device-side; exits at once when it is 1)."""
+        """One multiply pass over the gradients in the fusion buffer by ``out[1]`` (device-side; exits at once when it
+        is 1).  Multi-tensor over the parameter spans, NOT the flat buffer: the alignment padding between spans must
+        stay zero whatever the multiplier is (0 * NaN after an fp16 overflow would poison every later bucket's
+        statistics)."""
         if self._closed:
             return
         st = torch.cuda.current_stream(self.device).cuda_stream
         for group in self.groups.values():
-            self.rt.ctx.scale_flat(group.flat.data_ptr(), group.total_elems, group.native_dtype, out.data_ptr() + 4, 0, st)
+            spans = self._spans_of(group)
+            self.rt.ctx.multi_scale(spans[0], spans[1], group.native_dtype, out.data_ptr() + 4, st)
+
+    def _spans_of(self, group):
+        """(pointers, element counts) of every parameter's slice of ``group``'s fusion buffer (cached)."""
+        cache = self.__dict__.setdefault("_span_cache", {})
+        if group.dtype not in cache:
+            ptrs, numels = [], []
+            for b in self.buckets:
+                if b.group is group:
+                    ptrs.extend(b.ptrs)
+                    numels.extend(b.numels)
+            cache[group.dtype] = (ptrs, numels)
+        return cache[group.dtype]
 
     def take_pending_multiplier(self):
         """The pending [total_norm, multiplier, found_inf] tensor of a deferred clip / unscale, handed to the fused
@@ -694,6 +728,9 @@ class GradReducer:
         return pending.out
 
     def clamp_(self, clip_value: float):
+        if self._pending_mult is not None:
+            self._pending_mult.apply()
+            self._pending_mult = None
         st = torch.cuda.current_stream(self.device).cuda_stream
         for group in self.groups.values():
             self.rt.ctx.clamp_flat(group.flat.data_ptr(), group.total_elems, group.native_dtype, clip_value, 0, st)
@@ -720,11 +757,12 @@ class GradReducer:
             for group in self.groups.values():
                 mine = [(p, ptr, nb) for b in self.buckets if b.group is group for p, ptr, nb in zip(b.params, b.ptrs, b.nbytes)]
                 srcs, slots, sizes = [p.data_ptr() for p, _, _ in mine], [ptr for _, ptr, _ in mine], [nb for _, _, nb in mine]
-                ctx.pack(srcs, slots, sizes, self.rt.use_bulk_pack, st)
+                bulk = self.rt.bulk_for(sum(sizes))
+                ctx.pack(srcs, slots, sizes, bulk, st)
                 algo = self._pick_algo(group.segment)
                 ctx.allreduce_bucket(group.segment.seg, 0, group.total_elems, group.native_dtype, 1.0, -1, 0, algo,
                                      native.CH_USER, self.blocks_for(algo), native.NO_STREAM, st)  # fmt: skip
-                ctx.pack(slots, srcs, sizes, self.rt.use_bulk_pack, st)
+                ctx.pack(slots, srcs, sizes, bulk, st)
                 torch._foreach_div_([p.data for p, _, _ in mine], float(self.world))  # the reference's `/= N`
                 group.flat.zero_()
 
@@ -741,16 +779,17 @@ class GradReducer:
         with torch.no_grad():
             for group in self.groups.values():
                 mine = [(p, ptr, nb) for b in self.buckets if b.group is group for p, ptr, nb in zip(b.params, b.ptrs, b.nbytes)]
+                bulk = self.rt.bulk_for(sum(nb for _, _, nb in mine))
                 if self.rank == src:
                     ctx.pack([p.data_ptr() for p, _, _ in mine], [ptr for _, ptr, _ in mine], [nb for _, _, nb in mine],
-                             self.rt.use_bulk_pack, st)  # fmt: skip
+                             bulk, st)  # fmt: skip
                 nbytes = group.total_elems * group.elem_size
                 ctx.pull(group.segment.seg, 0, nbytes, group.flat.data_ptr(), 0, src, 1, native.CH_USER, 0, st)
                 for p, _, _ in mine:
                     if not p.is_contiguous():
                         raise ValueError("non-contiguous parameters are not supported by the B200 reducer")
                 ctx.pack([ptr for _, ptr, _ in mine], [p.data_ptr() for p, _, _ in mine], [nb for _, _, nb in mine],
-                         self.rt.use_bulk_pack, st)  # fmt: skip
+                         bulk, st)  # fmt: skip
                 group.flat.zero_()
 
     def remove_hooks(self):

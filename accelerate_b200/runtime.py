@@ -95,7 +95,11 @@ class SymmRuntime:
         self.staging: Segment | None = None
         self.staging_bytes = max(int(os.environ.get("B200DP_STAGING_MB", "64")) << 20, 2 * self.ctx.push_area_bytes())
         self.push_max = self.ctx.push_max_bytes() if os.environ.get("B200DP_PUSH", "1") != "0" else 0
-        self.use_bulk_pack = os.environ.get("B200DP_BULK_PACK", "1") != "0"
+        # bucket pack variant: "auto" (default) = the TMA-engine kernel for launches of >= 128 MiB (6.4 TB/s at 1 GB vs 5.8
+        # for LDG/STG), the LDG/STG kernel below (5.2 vs 4.5 TB/s on a 48 MB bucket, no shared memory: co-resides with the
+        # backward GEMMs it overlaps) — profiles/r02_pack_sweep_n1.jsonl; "1" / "0" force one of them
+        self.bulk_pack_mode = os.environ.get("B200DP_BULK_PACK", "auto").lower()
+        self.bulk_pack_min_bytes = int(os.environ.get("B200DP_BULK_PACK_MIN_MB", "128")) << 20
 
         # ---- collective agreement on the handle kind / multicast ----
         want = os.environ.get("B200DP_SEG_KIND", "fd").lower()
@@ -173,6 +177,16 @@ class SymmRuntime:
 
     def _all_ok(self, ok: bool) -> bool:
         return all(self._all_gather_object(bool(ok)))
+
+    @property
+    def use_bulk_pack(self) -> bool:
+        """Variant for launches whose size is not known to the caller (kept for the staging helpers: small copies)."""
+        return self.bulk_pack_mode == "1"
+
+    def bulk_for(self, nbytes: int) -> bool:
+        if self.bulk_pack_mode in ("0", "1"):
+            return self.bulk_pack_mode == "1"
+        return nbytes >= self.bulk_pack_min_bytes
 
     # ------------------------------------------------------------------ slots
     def reserve_slots(self, n: int) -> int:

@@ -223,6 +223,8 @@ def cpu_leg(model_name, steps, warmup, budget_s=25.0, micro_batch=1):
             sys.path.insert(0, REF_DIR)
             import accelerate as ref_accelerate
 
+            # the GPU comparison leg may have initialised the reference's singletons for CUDA in this process
+            ref_accelerate.state.AcceleratorState._reset_state(reset_partial_state=True)
             ref_acc = ref_accelerate.Accelerator(cpu=True, mixed_precision="bf16")
             model, opt = ref_acc.prepare(model, opt)
             kind = "reference"
@@ -828,7 +830,7 @@ def pack_probe(rt, fresh, st, hbm_peak, dsts=None):
             dsts.append(off)
             off += (n + 31) // 32 * 32
     srcs = [f.data_ptr() for f in fresh]
-    out = {"bucket_bytes": total, "tensors": len(fresh), "default": "bulk_tma" if rt.use_bulk_pack else "ldg_stg"}
+    out = {"bucket_bytes": total, "tensors": len(fresh), "default": "bulk_tma" if rt.bulk_for(total) else "ldg_stg"}
     for label, bulk in (("bulk_tma", 1), ("ldg_stg", 0)):
         t = event_time(lambda: rt.ctx.pack(srcs, dsts, nbytes, bulk, st))
         out[label] = {"ms": t, "GBps": 2 * total / (t * 1e-3) / 1e9, "frac_of_hbm_peak": 2 * total / (t * 1e-3) / 1e9 / hbm_peak}

@@ -179,10 +179,41 @@ def main():
         return [("fwd", fwd), ("bwd", bwd), ("clip", lambda: acc.clip_grad_norm_(model.parameters(), 1.0)),
                 ("opt", opt.step), ("zero", opt.zero_grad)]  # fmt: skip
 
+    def cpu_phase_times(step_phases, steps=12):
+        """Host time spent INSIDE each phase call (no synchronisation: pure enqueue cost) next to the GPU time per step,
+        without any profiler attached.  If the sum of the host times is close to the step time, the step is
+        launch-bound and only host-side savings show up in the throughput."""
+        import time
+
+        for _ in range(3):
+            for _, fn in step_phases:
+                fn()
+        torch.cuda.synchronize()
+        acc.wait_for_everyone()
+        host = {name: 0.0 for name, _ in step_phases}
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        t_all = time.perf_counter()
+        for _ in range(steps):
+            for name, fn in step_phases:
+                t0 = time.perf_counter()
+                fn()
+                host[name] += time.perf_counter() - t0
+        t_all = time.perf_counter() - t_all
+        e.record()
+        torch.cuda.synchronize()
+        out = {name: round(v / steps * 1e3, 3) for name, v in host.items()}
+        out["host_total_ms"] = round(t_all / steps * 1e3, 3)
+        out["gpu_step_ms"] = round(s.elapsed_time(e) / steps, 3)
+        return out
+
     def run(tag, step_phases):
         acc.wait_for_everyone()
+        host = cpu_phase_times(step_phases)
         events = trace_steps(step_phases, 3, args.warmup)
         result[tag] = analyse(events, 1)
+        if result[tag] is not None:
+            result[tag]["host_enqueue_ms_per_phase (no profiler)"] = host
         acc.wait_for_everyone()
 
     run("ours", phases(contextlib.nullcontext))
@@ -236,6 +267,7 @@ def main():
                         f.write(f"   {ph:5s} start {v['start_us']:9.0f}  span {v['span_us']:9.0f}  busy {v['busy_us']:9.0f}  kernels {v['kernels']}\n")
                     if "backward" in r:
                         f.write(f"   backward: {json.dumps(r['backward'])}\n")
+                    f.write(f"   host enqueue ms/phase (no profiler): {json.dumps(r.get('host_enqueue_ms_per_phase (no profiler)'))}\n")
                     for name, agg in sorted(r["own_kernel_totals_us"].items(), key=lambda kv: -kv[1]["us"]):
                         f.write(f"   own {name:50s} n={agg['n']:3d}  total {agg['us']:9.1f} us  stream {agg['stream']}\n")
                     for k in r.get("side_stream_timeline", []):

@@ -225,6 +225,21 @@ int b200dp_pack(b200dp_ctx* ctx, const void* const* srcs, void* const* dsts, con
 int b200dp_pull(b200dp_ctx* ctx, int seg, size_t byte_off, size_t nbytes, void* dst,
                 size_t dst_stride, int first, int nranks, int channel, int max_blocks, void* stream);
 
+/* ---- K2c: fused large-message allgather: stage + pull in ONE launch -----------------------------
+ * Replaces: torch.distributed.all_gather_into_tensor on a tensor that lives in ordinary torch memory
+ * (src/accelerate/utils/operations.py:337-343).  CTA b copies ITS portion of `src` into this rank's copy of
+ * `seg` at byte_off, meets CTA b of every rank at a flag barrier and pulls that portion from every rank into
+ * dst + r*dst_stride: no separate pack launch, no grid-wide barrier.  nbytes <= capacity of the window. */
+int b200dp_gather(b200dp_ctx* ctx, int seg, size_t byte_off, const void* src, size_t nbytes, void* dst,
+                  size_t dst_stride, int channel, int max_blocks, void* stream);
+
+/* ---- K1c: fused large-message out-of-place allreduce: stage + reduce-scatter + all-gather + copy-out in ONE
+ * launch.  Replaces: clone + torch.distributed.all_reduce(SUM) (+ `/= N`) (operations.py:859-874).
+ * dst = sum_r src_r (rank order, fp32 accumulate; NVLS: switch order), then T(float(T(sum)) / divisor) if
+ * divisor != 1.  src is never written.  f32 / bf16 / f16; algo TWOSHOT, NVLS or AUTO. */
+int b200dp_reduce(b200dp_ctx* ctx, int seg, size_t byte_off, const void* src, size_t count, int dtype,
+                  double divisor, void* dst, int algo, int channel, int max_blocks, void* stream);
+
 /* ---- K2b: latency path (one launch, one barrier) for messages up to b200dp_push_max_bytes() per rank.
  * Replaces all_gather_into_tensor / all_reduce for small tensors (operations.py:342,871).  The last
  * b200dp_push_area_bytes() bytes of segment `seg` are used as per-CTA, double-buffered windows, so

@@ -107,7 +107,9 @@ def main():
             ref = [p.grad.detach().clone() for p in model.parameters()]
             tn = acc.clip_grad_norm_(model.parameters(), 0.01)
             want = torch.sqrt(sum((g.double() ** 2).sum() for g in ref)).item()
-            assert acc.last_clip_mode == "fused" and abs(tn.item() - want) <= 1e-5 * want, (name, tn.item(), want)
+            # a user hook owns the communication: the fused kernel's statistics do not exist, the norm is recomputed
+            mode = "multi_tensor" if model.reducer.user_hook is not None else "fused"
+            assert acc.last_clip_mode == mode and abs(tn.item() - want) <= 1e-5 * want, (name, acc.last_clip_mode, tn.item(), want)
         if name == "user_allreduce":
             assert hook_state["calls"] == 2 * len(model.reducer.buckets)
     if all_hooks:

@@ -83,3 +83,11 @@ def test_three_ranks_two_shot_bit_exact():
     in the last ulp): bit-exact vs the oracle at N=3."""
     out = run_distributed("dist_allreduce_check.py", 3, env=ENV, timeout=600)
     assert out.count("ALLREDUCE_CHECK_OK") == 3, out[-3000:]
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_large_gather_and_reduce_fused_kernels(world):
+    """accelerator.gather / reduce above the latency path: one fused launch per staging window (b200dp_gather /
+    b200dp_reduce), ragged sizes, odd source offsets, all float dtypes, mean, > window (32 MiB staging forces chunking)."""
+    out = run_distributed("dist_collectives_large.py", world, env=dict(ENV, B200DP_STAGING_MB="32"), timeout=900)
+    assert out.count("COLLECTIVES_LARGE_OK") == world, out[-3000:]
