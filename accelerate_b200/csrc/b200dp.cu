@@ -166,7 +166,6 @@ struct b200dp_ctx {
   int next_event = 0;
   std::atomic<unsigned long long> launches{0};
   int fdx_sock = -1;
-  bool bulk_attr_set = false;
 };
 
 extern "C" int b200dp_version(void) { return B200DP_VERSION; }
@@ -1013,7 +1012,8 @@ extern "C" int b200dp_multi_adam(b200dp_ctx* c, void* const* params, const void*
 // ------------------------------------------------------------------------------------------------
 // K4
 // ------------------------------------------------------------------------------------------------
-static void pack_push(PackTable* t, int* n, uint32_t* acc, const char* s, char* d, size_t bytes) {
+template <typename Table>
+static void pack_push(Table* t, int* n, uint32_t* acc, const char* s, char* d, size_t bytes) {
   t->src[*n] = s;
   t->dst[*n] = d;
   t->bytes[*n] = bytes;
@@ -1046,39 +1046,39 @@ static BulkCfg bulk_cfg() {
   return cfg;
 }
 
-extern "C" int b200dp_pack(b200dp_ctx* c, const void* const* srcs, void* const* dsts, const size_t* nbytes, int n,
-                           int use_bulk, void* stream) {
-  if (!c || (n > 0 && (!srcs || !dsts || !nbytes))) return fail(B200DP_EINVAL, "null argument");
-  DeviceGuard g(c->device);
-  cudaStream_t st = (cudaStream_t)stream;
-  static thread_local PackTable bulk, plain;
+template <int CAP>
+static int pack_impl(b200dp_ctx* c, const void* const* srcs, void* const* dsts, const size_t* nbytes, int n, int use_bulk,
+                     cudaStream_t st) {
+  using Table = PackTableT<CAP>;
+  static thread_local Table bulk, plain;
   const BulkCfg cfg = bulk_cfg();
   bulk.chunk_bytes = uint32_t(cfg.stage_bytes);
   plain.chunk_bytes = kPackChunk;
   int nb = 0, np = 0;
   uint32_t accb = 0, accp = 0;
   auto flush = [&](bool force) -> int {
-    if (nb > 0 && (force || nb >= kMTMax - 1)) {
+    if (nb > 0 && (force || nb >= CAP - 1)) {
       bulk.chunk_start[nb] = accb;
       bulk.n = nb;
       const size_t smem = size_t(cfg.warps) * cfg.stages * cfg.stage_bytes;
-      if (!c->bulk_attr_set) {
-        RT(cudaFuncSetAttribute(pack_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        c->bulk_attr_set = true;
+      static bool attr_set = false;  // per instantiation
+      if (!attr_set) {
+        RT(cudaFuncSetAttribute(pack_bulk_kernel<CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        attr_set = true;
       }
       int want = int((accb + cfg.warps - 1) / cfg.warps);
       int cap = c->sm_count * cfg.ctas_per_sm;
       int grid = want < cap ? want : cap;
-      pack_bulk_kernel<<<grid, cfg.warps * 32, smem, st>>>(bulk, c->d_status, cfg.stages);
+      pack_bulk_kernel<CAP><<<grid, cfg.warps * 32, smem, st>>>(bulk, c->d_status, cfg.stages);
       KERNEL_OK(c);
       nb = 0;
       accb = 0;
     }
-    if (np > 0 && (force || np >= kMTMax - 2)) {
+    if (np > 0 && (force || np >= CAP - 2)) {
       plain.chunk_start[np] = accp;
       plain.n = np;
       int grid = int(accp) < c->sm_count * 8 ? int(accp) : c->sm_count * 8;
-      pack_kernel<<<grid, kStreamThreads, 0, st>>>(plain);
+      pack_kernel<CAP><<<grid, kStreamThreads, 0, st>>>(plain);
       KERNEL_OK(c);
       np = 0;
       accp = 0;
@@ -1102,6 +1102,16 @@ extern "C" int b200dp_pack(b200dp_ctx* c, const void* const* srcs, void* const* 
     if (rc) return rc;
   }
   return flush(true);
+}
+
+extern "C" int b200dp_pack(b200dp_ctx* c, const void* const* srcs, void* const* dsts, const size_t* nbytes, int n,
+                           int use_bulk, void* stream) {
+  if (!c || (n > 0 && (!srcs || !dsts || !nbytes))) return fail(B200DP_EINVAL, "null argument");
+  DeviceGuard g(c->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  // a gradient bucket (~10 tensors) fits the small table: ~0.9 KB of kernel parameters instead of ~18 KB
+  if (n <= kPackSmall - 2) return pack_impl<kPackSmall>(c, srcs, dsts, nbytes, n, use_bulk, st);
+  return pack_impl<kMTMax>(c, srcs, dsts, nbytes, n, use_bulk, st);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -693,14 +693,20 @@ __global__ void __launch_bounds__(kThreads, 1) push_kernel(const PushArgs a) {
 // ------------------------------------------------------------------------------------------------
 // K4: multi-tensor copy (bucket pack / unpack / staging).  One launch for a whole bucket.
 // ------------------------------------------------------------------------------------------------
-struct PackTable {
-  const char* src[kMTMax];
-  char* dst[kMTMax];
-  unsigned long long bytes[kMTMax];
-  uint32_t chunk_start[kMTMax + 1];  // prefix sum of ceil(bytes / chunk_bytes)
-  uint32_t chunk_bytes;              // work unit: kPackChunk (LDG/STG) or one TMA stage (bulk)
+// CAP = table capacity.  The table travels as a kernel parameter; a gradient bucket holds ~10 tensors, and launching with
+// a 900-byte table instead of an 18 KB one is several microseconds cheaper on the (host-bound) autograd thread.
+template <int CAP>
+struct PackTableT {
+  const char* src[CAP];
+  char* dst[CAP];
+  unsigned long long bytes[CAP];
+  uint32_t chunk_start[CAP + 1];  // prefix sum of ceil(bytes / chunk_bytes)
+  uint32_t chunk_bytes;           // work unit: kPackChunk (LDG/STG) or one TMA stage (bulk)
   int n;
 };
+constexpr int kPackSmall = 32;
+using PackTable = PackTableT<kMTMax>;
+using PackTableSmall = PackTableT<kPackSmall>;
 
 __device__ __forceinline__ int find_tensor(const uint32_t* chunk_start, int n, uint32_t chunk) {
   int lo = 0, hi = n;  // last t with chunk_start[t] <= chunk
@@ -715,7 +721,8 @@ __device__ __forceinline__ int find_tensor(const uint32_t* chunk_start, int n, u
 // before the first store of a trip (256 threads x 4 x 16 B = 16 KB per CTA, x up to 8 CTAs per SM), which is what
 // covers HBM latency; no shared memory and few registers, so it co-resides with the backward GEMMs it overlaps.
 constexpr int kPackILP = 4;
-__global__ void __launch_bounds__(kStreamThreads) pack_kernel(const __grid_constant__ PackTable t) {
+template <int CAP>
+__global__ void __launch_bounds__(kStreamThreads) pack_kernel(const __grid_constant__ PackTableT<CAP> t) {
   const uint32_t total = t.chunk_start[t.n];
   const size_t chunk_bytes = t.chunk_bytes;
   for (uint32_t c = blockIdx.x; c < total; c += gridDim.x) {
@@ -796,7 +803,8 @@ constexpr int kBulkMaxWarps = 8;
 constexpr int kBulkMaxStages = 8;
 
 // All spans must be 16-byte aligned with a size that is a multiple of 16 (the host splits off the rest).
-__global__ void __launch_bounds__(kBulkMaxWarps * 32) pack_bulk_kernel(const __grid_constant__ PackTable t, int* status,
+template <int CAP>
+__global__ void __launch_bounds__(kBulkMaxWarps * 32) pack_bulk_kernel(const __grid_constant__ PackTableT<CAP> t, int* status,
                                                                         int stages) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t full_all[kBulkMaxWarps][kBulkMaxStages];

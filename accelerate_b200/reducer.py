@@ -102,7 +102,7 @@ def compute_bucket_assignment(sizes_bytes, keys, first_cap: int, cap: int):
 class GradBucket:
     __slots__ = (
         "index", "group", "elem_off", "count", "params", "offsets", "numels", "views", "ptrs", "nbytes",
-        "pending", "seen", "staged", "slot", "flat", "c_ptrs", "c_nbytes",
+        "pending", "seen", "staged", "slot", "flat", "c_ptrs", "c_nbytes", "fired", "trigger", "handles", "missed",
     )  # fmt: skip
 
     def __init__(self, index, group):
@@ -115,11 +115,16 @@ class GradBucket:
         self.slot = -1
         self.flat = None
         self.c_ptrs = self.c_nbytes = None  # ctypes arrays of ptrs / nbytes, built once (CUDA)
+        self.fired = []  # fast hooks: parameters whose gradient was accumulated in this backward (list.append IS the hook)
+        self.trigger = -1  # index of the parameter expected to fire last (learned); its hook is the only Python one
+        self.handles = []
+        self.missed = False
 
     def reset(self):
         self.pending = len(self.params)
         for i in range(len(self.seen)):
             self.seen[i] = False
+        self.fired.clear()  # never rebound: `fired.append` is registered as a hook
 
 
 class HookBucket:
@@ -275,10 +280,16 @@ class GradReducer:
                 b.c_nbytes = (ctypes.c_size_t * len(b.nbytes))(*b.nbytes)
         self._managed_ids = frozenset(id(p) for p in params)
         self._param_index = {id(p): k for k, p in enumerate(params)}
-        self._hooks = []
+        # Hooks run on the autograd thread, and the backward of an eager transformer is host-bound (the engine enqueues
+        # slower than the GPU executes: profiles/r02_timeline_n2.txt), so every microsecond here is a microsecond of step
+        # time.  Fast hooks: the hook of all parameters but one per bucket is the C-level `list.append` of the bucket's
+        # `fired` list; only the parameter expected to fire LAST (learned from the previous iteration) runs Python.
+        self._fast = (not find_unused_parameters) and os.environ.get("B200DP_FAST_HOOKS", "1") != "0"
+        self._relearn = []
         for b in self.buckets:
-            for i, p in enumerate(b.params):
-                self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(b, i)))
+            if self._fast:
+                b.trigger = len(b.params) - 1  # bucket order is reverse registration order ~ gradient-ready order
+            self._install_bucket_hooks(b)
         self._reset_iteration()
         _LIVE.add(self)
 
@@ -312,10 +323,69 @@ class GradReducer:
 
         return hook
 
+    def _install_bucket_hooks(self, b: GradBucket):
+        for h in b.handles:
+            h.remove()
+        b.handles = []
+        for i, p in enumerate(b.params):
+            if not self._fast:
+                fn = self._make_hook(b, i)
+            elif i == b.trigger:
+                fn = self._make_trigger(b)
+            else:
+                fn = b.fired.append  # returns None, takes the parameter: a valid post-accumulate-grad hook at C speed
+            b.handles.append(p.register_post_accumulate_grad_hook(fn))
+
+    def _make_trigger(self, bucket: GradBucket):
+        fired = bucket.fired
+
+        def trigger(param):
+            fired.append(param)
+            if not self._armed:
+                self.stats_valid = False  # gradients changed outside a reduction (see `hook`)
+                fired.clear()
+                return
+            if not self._cb_queued:
+                self._cb_queued = True
+                Variable._execution_engine.queue_callback(self._on_graph_task_end)
+            self._launch_ready()
+            if bucket.index >= self._next and not bucket.missed:
+                # the expected-last parameter was not the last one this time: the bucket goes out with a later trigger
+                # (or at the end of backward); learn the real order for the next iteration
+                bucket.missed = True
+                self._relearn.append(bucket)
+
+        return trigger
+
+    def _complete(self, b: GradBucket) -> bool:
+        """Fast hooks: has every parameter of ``b`` fired in this backward?  If so adopt the gradients (what the
+        per-parameter Python hook does one by one) and mark the bucket ready."""
+        n = len(b.params)
+        fired = b.fired
+        if len(fired) < n or (len(fired) > n and len({id(p) for p in fired}) < n):
+            return False
+        if b.missed:
+            last = fired[-1]
+            b.trigger = next(i for i, p in enumerate(b.params) if p is last)
+        staged, ptrs, views = b.staged, b.ptrs, b.views
+        for i, p in enumerate(b.params):
+            g = raw_grad(p)
+            if g is not views[i] and g is not None and g.data_ptr() != ptrs[i]:
+                staged.append((i, g if g.is_contiguous() else g.contiguous()))
+                raw_set_grad(p, views[i])
+        seen = b.seen
+        for i in range(n):
+            seen[i] = True
+        b.pending = 0
+        return True
+
     def _launch_ready(self):
         buckets = self.buckets
-        while self._next < len(buckets) and buckets[self._next].pending == 0:  # strictly in index order
-            self._reduce_bucket(buckets[self._next])
+        while self._next < len(buckets):  # strictly in index order
+            b = buckets[self._next]
+            if b.pending != 0 and not (self._fast and self._complete(b)):
+                break
+            self._reduce_bucket(b)
             self._next += 1
 
     # ------------------------------------------------------------------ the data path
@@ -324,6 +394,7 @@ class GradReducer:
             ctx = self.rt.ctx
             cs = self.compute_stream
             comm = cs if _SAME_STREAM else self.comm_stream
+            packed_on_comm = False
             if b.staged:
                 srcs = [g.data_ptr() for _, g in b.staged]
                 if len(b.staged) == len(b.ptrs) and all(i == k for k, (i, _) in enumerate(b.staged)):
@@ -340,6 +411,7 @@ class GradReducer:
                     ctx.pack(srcs, dsts, sizes, self.rt.bulk_for(b.count * b.group.elem_size), comm)
                     self._graveyard.extend(g for _, g in b.staged)
                     pack_stream = comm
+                    packed_on_comm = True
                 else:
                     ctx.pack(srcs, dsts, sizes, self.rt.bulk_for(b.count * b.group.elem_size), cs)
                     pack_stream = cs
@@ -359,8 +431,10 @@ class GradReducer:
             # measured on B200 (profiles/): with 2 ranks the switch has nothing to save and plain peer
             # loads/stores stream faster; from 4 ranks on NVLS moves ~S instead of 2(N-1)/N*S per GPU
             algo = self._pick_algo(seg)
+            # (a pack on the side stream already ordered that stream behind the compute stream)
+            after = native.NO_STREAM if (packed_on_comm or comm == cs) else cs
             ctx.allreduce_bucket(seg.seg, b.elem_off, b.count, b.group.native_dtype, 1.0 / self.world, b.slot,
-                                 native.F_STATS | native.F_NO_END_BARRIER, algo, native.CH_GRAD, self.blocks_for(algo), cs,
+                                 native.F_STATS | native.F_NO_END_BARRIER, algo, native.CH_GRAD, self.blocks_for(algo), after,
                                  comm)  # fmt: skip
             self._comm_dirty = True
         else:
@@ -488,12 +562,14 @@ class GradReducer:
         """Safety net for a backward whose last gradient hook ran in a nested graph task that could not know it was
         the last (reentrant checkpointing + parameters left unused): finish the reduction before anybody consumes
         the gradients.  A no-op in every ordinary run."""
-        if self._armed and not self._cb_queued and any(any(b.seen) for b in self.buckets):
+        if self._armed and not self._cb_queued and any(any(b.seen) or b.fired for b in self.buckets):
             self._finalize_backward()
 
     def _finalize_backward(self):
         """Runs once per sync backward, after its last gradient."""
         try:
+            if self._next < len(self.buckets) and self._fast:
+                self._launch_ready()  # buckets whose learned trigger fired early are complete by now
             if self._next < len(self.buckets):
                 self._handle_unready()
             if self._hook_futures:
@@ -536,6 +612,17 @@ class GradReducer:
             self._reset_iteration()
 
     def _handle_unready(self):
+        if self._fast:  # the per-parameter bookkeeping lives in `fired`
+            for b in self.buckets[self._next :]:
+                ids = {id(p) for p in b.fired}
+                for i, p in enumerate(b.params):
+                    if id(p) in ids and not b.seen[i]:
+                        g = raw_grad(p)
+                        if g is not b.views[i] and g is not None and g.data_ptr() != b.ptrs[i]:
+                            b.staged.append((i, g if g.is_contiguous() else g.contiguous()))
+                            raw_set_grad(p, b.views[i])
+                        b.seen[i] = True
+                        b.pending -= 1
         missing = [(b, i) for b in self.buckets[self._next :] for i in range(len(b.params)) if not b.seen[i]]
         if missing and not self.find_unused_parameters:
             names = {id(p): n for n, p in self.owner.module.named_parameters()}
@@ -610,6 +697,11 @@ class GradReducer:
         self._cb_queued = False
         for b in self.buckets:
             b.reset()
+        if self._relearn:
+            relearn, self._relearn = self._relearn, []
+            for b in relearn:
+                b.missed = False
+                self._install_bucket_hooks(b)  # b.trigger was updated when the bucket completed
 
     # ------------------------------------------------------------------ API the wrapper / Accelerator use
     def prepare_for_backward(self, unused=None):
@@ -793,9 +885,10 @@ class GradReducer:
                 group.flat.zero_()
 
     def remove_hooks(self):
-        for h in self._hooks:
-            h.remove()
-        self._hooks = []
+        for b in self.buckets:
+            for h in b.handles:
+                h.remove()
+            b.handles = []
 
     def close(self):
         """Release everything the reducer took from the runtime: autograd hooks, the symmetric fusion / wire

@@ -575,39 +575,70 @@ def parity_block(args, acc, rt, rank, world, dev):
                                    "what": "reduce(L_r + 0) vs sum_r fl(L_r/N) in rank order; bit-exact required for two-shot, "
                                            "float32-rounding close for NVLS (switch-order sum)"}  # fmt: skip
     exact_ok = (bad_exact == 0) if algo == "twoshot" else (viol == 0)
-    r2_vs_r1 = max((a - p.grad).abs().max().item() for a, p in zip(r1, params))
-    result["repeat_backward_max_abs"] = r2_vs_r1  # two backwards of the same batch differ only by atomics order (wte)
-    del local
+    r2 = [p.grad.detach().clone() for p in params]
+    # noise floor of the comparison itself: two backward passes of THIS model on the same batch (bf16 autocast, atomics
+    # in the embedding / attention backward) do not produce the same local gradients bit for bit
+    nf_abs, nf_bad = 0.0, 0
+    for a, b_ in zip(r1, r2):
+        diff = (a - b_).abs()
+        nf_abs = max(nf_abs, diff.max().item())
+        nf_bad += int((diff > 1e-5 + 1e-3 * b_.abs()).sum().item())
+    result["repeat_backward_noise_floor"] = {"max_abs": nf_abs, "elements_outside_tolerance": nf_bad,
+                                             "what": "ours vs ours, two backward passes of the same batch: what any comparison of "
+                                                     "independently computed gradients is subject to"}  # fmt: skip
     ours.reducer.close()
     acc._wrappers = [w for w in acc._wrappers if w is not ours]
     acc._models = [m for m in acc._models if m is not ours.module]
     del ours
     torch.cuda.empty_cache()
 
-    # ---- (3) stock torch DDP + NCCL on the same weights and batch ----
+    # ---- (3) stock torch DDP + NCCL ----
     vs_ddp = {"unavailable": "needs one GPU per rank (NCCL)"}
     ddp_ok = True
     if nccl:
         ref = torch.nn.parallel.DistributedDataParallel(build_model(name, dropout=0.0).to(dev), device_ids=[dev.index], bucket_cap_mb=25)
         ref.train()
+        rparams = list(ref.module.parameters())
+
+        def compare(ours_list, rtol, atol):
+            m_abs = m_rel = 0.0
+            bad = total = 0
+            for a, q in zip(ours_list, rparams):
+                b_ = q.grad
+                diff = (a - b_).abs()
+                m_abs = max(m_abs, diff.max().item())
+                m_rel = max(m_rel, (diff / b_.abs().clamp_min(1e-5)).max().item())
+                bad += int((diff > atol + rtol * b_.abs()).sum().item())
+                total += b_.numel()
+            return {"max_abs": m_abs, "max_rel_over_floor_1e-5": m_rel, "elements_outside_tolerance": bad, "elements": total}
+
+        # (3a) the reduction alone: BOTH wrappers reduce the very same local gradients L_r.  DDP gets them as pre-existing
+        # .grad (what a no_sync micro-step leaves behind) and reduces L_r + 0 in a sync backward of 0 * loss — its own
+        # bucket copy-in, ncclAllReduce and copy-back (accelerator.py:1892-1894 -> torch reducer.cpp).
+        for q, mine in zip(rparams, local):
+            q.grad = mine.clone()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = forward_loss(ref, ids, name) * 0.0
+        loss.float().backward()
+        torch.cuda.synchronize()
+        same = compare(r2, 1e-3, 1e-5)
+        same["what"] = ("same local gradients through both wrappers: B200DataParallel vs torch DistributedDataParallel(bucket_cap_mb=25) "
+                        "+ NCCL, rtol 1e-3 / atol 1e-5 (north star); isolates the reduction from backward non-determinism")  # fmt: skip
+        # (3b) end to end: an independent forward/backward through DDP on the same weights and batch (subject to the
+        # noise floor above, reported for completeness; not part of the verdict)
+        for q in rparams:
+            q.grad = None
         with torch.autocast("cuda", dtype=torch.bfloat16):
             loss = forward_loss(ref, ids, name)
         loss.float().backward()
         torch.cuda.synchronize()
-        m_abs = m_rel = 0.0
-        bad = total = 0
-        for a, q in zip(r1, ref.module.parameters()):
-            b = q.grad
-            diff = (a - b).abs()
-            m_abs = max(m_abs, diff.max().item())
-            m_rel = max(m_rel, (diff / b.abs().clamp_min(1e-5)).max().item())
-            bad += int((diff > 1e-5 + 1e-3 * b.abs()).sum().item())
-            total += b.numel()
-        vs_ddp = {"max_abs": m_abs, "max_rel_over_floor_1e-5": m_rel, "elements_outside_tolerance": bad, "elements": total,
-                  "what": "torch.nn.parallel.DistributedDataParallel(bucket_cap_mb=25) + NCCL, torch.autocast(bf16), same weights/batch"}  # fmt: skip
-        ddp_ok = bad == 0
-        del ref
+        indep = compare(r1, 1e-3, 1e-5)
+        indep["what"] = "independent forward/backward through each wrapper (same weights, batch, dropout 0): includes the noise floor"
+        vs_ddp = {"same_local_gradients": same, "independent_backward": indep}
+        ddp_ok = same["elements_outside_tolerance"] == 0
+        del ref, rparams
         torch.cuda.empty_cache()
+    del local, r1, r2
     result["vs_torch_ddp_nccl"] = vs_ddp
     flags = torch.tensor([int(result["all_ranks_bit_identical"]), int(exact_ok), int(ddp_ok)], device=dev)
     flags = acc.gather(flags.reshape(1, 3)).min(dim=0).values  # every rank must agree
@@ -760,11 +791,14 @@ def kernel_roofline(acc, model, rt, world, peaks, peak_src):
     span = min(256 << 20, group.total_elems * 4 // 16 * 16)
     sink = torch.empty(span, dtype=torch.uint8, device=dev)
     nbr = (acc.process_index + 1) % world
-    t_copy = clock(lambda _: rt.ctx.pull(group.segment.seg, 0, span, sink.data_ptr(), 0, nbr, 1, native.CH_USER, 0, st), None)
-    nvlink_peak = span / (t_copy * 1e-3) / 1e9
-    extra["nvlink_peer_copy"] = {"GBps_per_direction": nvlink_peak, "bytes": span, "ms": t_copy,
+    by_ctas = {}
+    for ctas in (16, 32, 64, 148):
+        t_copy = clock(lambda _: rt.ctx.pull(group.segment.seg, 0, span, sink.data_ptr(), 0, nbr, 1, native.CH_USER, ctas, st), None)
+        by_ctas[ctas] = span / (t_copy * 1e-3) / 1e9
+    nvlink_peak = max(by_ctas.values())
+    extra["nvlink_peer_copy"] = {"GBps_per_direction": nvlink_peak, "bytes": span, "GBps_by_ctas": by_ctas,
                                  "how": "pull_kernel: every rank reads 256 MiB from rank+1's symmetric segment into local HBM, all "
-                                        "ranks at once (each GPU's links carry one stream in and one out); max over ranks"}  # fmt: skip
+                                        "ranks at once (each GPU's links carry one stream in and one out); best CTA count, max over ranks"}  # fmt: skip
     del sink
 
     counters = NvlinkCounters(dev)

@@ -22,6 +22,10 @@ def _fresh_state():
     AcceleratorState._reset_state()
     GradientState._reset_state()
     # PartialState (process group / native runtime) survives: one per test process
+    from accelerate_b200 import lazy_grad
+
+    for pending in list(lazy_grad._pending):  # a deferred clip nobody consumed must not leak into the next test
+        pending.discard()
 
 
 import threading  # noqa: E402

@@ -91,3 +91,11 @@ def test_large_gather_and_reduce_fused_kernels(world):
     b200dp_reduce), ragged sizes, odd source offsets, all float dtypes, mean, > window (32 MiB staging forces chunking)."""
     out = run_distributed("dist_collectives_large.py", world, env=dict(ENV, B200DP_STAGING_MB="32"), timeout=900)
     assert out.count("COLLECTIVES_LARGE_OK") == world, out[-3000:]
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_save_state_load_state_resume_cuda(world):
+    """SURVEY.md §8f row 4 on the GPU path: mid-run save_state, resume into fresh objects, replay == uninterrupted run
+    bit for bit (weights, fused-Adam moments and step counters, scheduler), reference file names on disk."""
+    out = run_distributed("dist_resume_gpu.py", world, env=ENV, timeout=600)
+    assert out.count("RESUME_GPU_OK") == world, out[-3000:]
