@@ -19,8 +19,14 @@ import torch
 from . import native
 from .runtime import SymmRuntime, native_dtype
 
+import os
+
 # below this many bytes per rank the out-of-place one-shot allreduce wins (latency bound)
 ONESHOT_MAX_BYTES = 512 * 1024
+# large messages: one fused launch per staging window (b200dp_gather / b200dp_reduce).  "0" selects the round-1 sequence
+# (pack -> pull / in-place allreduce -> pack) that the fused kernels are measured against (benchmarks/collective_sweep.py).
+FUSED_GATHER = os.environ.get("B200DP_FUSED_GATHER", "1") != "0"
+FUSED_REDUCE = os.environ.get("B200DP_FUSED_REDUCE", "1") != "0"
 
 
 def _bulk_capacity(rt, staging) -> int:
@@ -65,7 +71,11 @@ def all_gather(t: torch.Tensor) -> torch.Tensor:
     done = 0
     while done < nbytes:
         n = min(cap, nbytes - done)
-        rt.ctx.gather(staging.seg, 0, src + done, n, dst + done, nbytes, native.CH_USER, 0, st)
+        if FUSED_GATHER:
+            rt.ctx.gather(staging.seg, 0, src + done, n, dst + done, nbytes, native.CH_USER, 0, st)
+        else:
+            rt.ctx.pack([src + done], [staging.ptr], [n], rt.bulk_for(n), st)
+            rt.ctx.pull(staging.seg, 0, n, dst + done, nbytes, 0, world, native.CH_USER, 0, st)
         done += n
     return out
 
@@ -102,16 +112,24 @@ def all_reduce(t: torch.Tensor, mean: bool = False) -> torch.Tensor:
     done = 0
     while done < numel:
         n = min(cap_elems, numel - done)
-        if large:
+        if large and FUSED_REDUCE:
             # ONE fused launch (b200dp_reduce): CTA b stages its portion, the owners reduce their share of it over all
             # ranks' staged copies (two-shot by peer loads, or NVLS in the switch) and write the result into every
             # rank's staging, CTA b copies its portion out — dividing on the way for "mean", like the reference's `/= N`
             rt.ctx.reduce(staging.seg, 0, src.data_ptr() + done * es, n, dt, divisor, out.data_ptr() + done * es, algo,
                           native.CH_USER, 0, st)  # fmt: skip
+        elif large:
+            nb = n * es
+            rt.ctx.pack([src.data_ptr() + done * es], [staging.ptr], [nb], rt.bulk_for(nb), st)
+            padded = (nb + 15) // 16 * 16 // es
+            rt.ctx.allreduce_bucket(staging.seg, 0, padded, dt, 1.0, -1, 0, algo, native.CH_USER, 0, native.NO_STREAM, st)
+            rt.ctx.pack([staging.ptr], [out.data_ptr() + done * es], [nb], rt.bulk_for(nb), st)
         else:
             rt.ctx.pack([src.data_ptr() + done * es], [staging.ptr], [n * es], rt.bulk_for(n * es), st)
             rt.ctx.allreduce_oneshot(staging.seg, 0, n, dt, divisor, out.data_ptr() + done * es, native.CH_USER, 0, st)
         done += n
+    if mean and large and not FUSED_REDUCE:
+        out /= world  # same op the reference applies (`/= N`)
     return out.view(t.shape)
 
 

@@ -1171,7 +1171,7 @@ extern "C" int b200dp_gather(b200dp_ctx* c, int seg, size_t byte_off, const void
   a.src = reinterpret_cast<const char*>(src);
   a.dst = reinterpret_cast<char*>(dst);
   a.dst_stride = dst_stride;
-  static const int dflt = env_blocks("B200DP_GATHER_BLOCKS", 32);
+  static const int dflt = env_blocks("B200DP_GATHER_BLOCKS", 148);  // staging + pull need the whole chip (r02 sweep)
   const int grid = clamp_blocks(c, (nbytes + 15) / 16, size_t(kThreads) * 4, max_blocks > 0 ? max_blocks : dflt);
   gather_fused_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);
   KERNEL_OK(c);
@@ -1226,7 +1226,7 @@ extern "C" int b200dp_reduce(b200dp_ctx* c, int seg, size_t byte_off, const void
   a.src = src;
   a.dst = dst;
   a.divisor = float(divisor);
-  static const int dflt = env_blocks("B200DP_REDUCE_FUSED_BLOCKS", 32);
+  static const int dflt = env_blocks("B200DP_REDUCE_FUSED_BLOCKS", 148);  // the local copy phases want every SM (r02 sweep)
   const int grid = clamp_blocks(c, (count * es + 15) / 16, size_t(kThreads) * 4, max_blocks > 0 ? max_blocks : dflt);
   cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {
@@ -1235,6 +1235,20 @@ extern "C" int b200dp_reduce(b200dp_ctx* c, int seg, size_t byte_off, const void
     default: launch_reduce<__half>(a, c->world, nvls, grid, st); break;
   }
   KERNEL_OK(c);
+  return B200DP_OK;
+}
+
+// copy-engine peer copy: the "what can this link do" yardstick the kernels are measured against
+extern "C" int b200dp_peer_copy(b200dp_ctx* c, int seg, int peer, size_t byte_off, void* dst, size_t nbytes, void* stream) {
+  Segment* s;
+  int rc = get_seg(c, seg, &s);
+  if (rc) return rc;
+  if (peer < 0 || peer >= c->world || !s->peer_mapped[peer]) return fail(B200DP_ESTATE, "peer %d of segment %d not mapped", peer, seg);
+  if (byte_off + nbytes > s->bytes) return fail(B200DP_EINVAL, "range exceeds segment");
+  if (!dst) return fail(B200DP_EINVAL, "dst is NULL");
+  DeviceGuard g(c->device);
+  RT(cudaMemcpyAsync(dst, reinterpret_cast<const char*>(s->peer[peer]) + byte_off, nbytes, cudaMemcpyDeviceToDevice,
+                     (cudaStream_t)stream));
   return B200DP_OK;
 }
 

@@ -477,11 +477,22 @@ __global__ void __launch_bounds__(kThreads, 1) gather_fused_kernel(const GatherA
   char* mine = reinterpret_cast<char*>(a.bufs.p[b.rank]) + a.byte_off + lo;
   copy_any(mine, a.src + lo, n, threadIdx.x, blockDim.x);
   cross_rank_barrier(b, base + 1);  // CTA b of every rank has staged portion b
-  // own block straight from the staged copy, then the peers, starting with the next rank (N readers, N sources)
-  for (int k = 0; k < b.world; ++k) {
+  // All N sources at once: the 16 warps split into (up to) N groups, group g copies from rank (rank + g) % N, so the
+  // local block (HBM) and every peer's block (NVLink) stream concurrently instead of one after the other, and each
+  // GPU serves its N - 1 readers evenly.  With more ranks than warps the groups take several sources in turn.
+  const int nwarps = blockDim.x >> 5;
+  const int groups = b.world < nwarps ? b.world : nwarps;
+  const int per_group = nwarps / groups;               // warps per group (the last group takes the remainder)
+  int gidx = (threadIdx.x >> 5) / per_group;
+  if (gidx >= groups) gidx = groups - 1;
+  const int gfirst = gidx * per_group;
+  const int gwarps = (gidx == groups - 1) ? nwarps - gfirst : per_group;
+  const size_t gtid = size_t(threadIdx.x) - size_t(gfirst) * 32;
+  const size_t gthreads = size_t(gwarps) * 32;
+  for (int k = gidx; k < b.world; k += groups) {
     const int r = (b.rank + k) % b.world;
-    copy_span(a.dst + size_t(r) * a.dst_stride + lo, reinterpret_cast<const char*>(a.bufs.p[r]) + a.byte_off + lo, n,
-              threadIdx.x, blockDim.x);
+    copy_span(a.dst + size_t(r) * a.dst_stride + lo, reinterpret_cast<const char*>(a.bufs.p[r]) + a.byte_off + lo, n, gtid,
+              gthreads);
   }
   // nobody may restage (next call) while a peer still reads this window
   cross_rank_barrier(b, base + 2);

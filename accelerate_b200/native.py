@@ -45,7 +45,7 @@ EXPORTS = [
     "b200dp_set_control", "b200dp_fdx_open", "b200dp_fdx_send", "b200dp_fdx_recv", "b200dp_fdx_close",
     "b200dp_stream_wait", "b200dp_fence", "b200dp_allreduce_bucket", "b200dp_allreduce_oneshot", "b200dp_finalize_norm",
     "b200dp_scale_flat", "b200dp_clamp_flat", "b200dp_cast", "b200dp_multi_stats", "b200dp_multi_scale", "b200dp_multi_adam", "b200dp_pack",
-    "b200dp_pull", "b200dp_gather", "b200dp_reduce", "b200dp_push_max_bytes", "b200dp_push_area_bytes", "b200dp_push", "b200dp_exchange_small",
+    "b200dp_pull", "b200dp_gather", "b200dp_reduce", "b200dp_peer_copy", "b200dp_push_max_bytes", "b200dp_push_area_bytes", "b200dp_push", "b200dp_exchange_small",
     "b200dp_pad_copy",
 ]  # fmt: skip
 
@@ -160,6 +160,7 @@ def load():
             "b200dp_pack": [vp, POINTER(vp), POINTER(vp), POINTER(sz), i, i, vp],
             "b200dp_pull": [vp, i, sz, sz, vp, sz, i, i, i, i, vp],
             "b200dp_gather": [vp, i, sz, vp, sz, vp, sz, i, i, vp],
+            "b200dp_peer_copy": [vp, i, i, sz, vp, sz, vp],
             "b200dp_reduce": [vp, i, sz, vp, sz, i, c_double, vp, i, i, i, vp],
             "b200dp_push": [vp, i, i, vp, sz, i, c_double, vp, i, vp],
             "b200dp_exchange_small": [vp, vp, i, vp, vp],
@@ -375,6 +376,9 @@ class Context:
             self.lib.b200dp_pull(self.h, seg, byte_off, nbytes, dst, dst_stride, first, nranks, channel, max_blocks, stream),
             "b200dp_pull",
         )
+
+    def peer_copy(self, seg, peer, byte_off, dst, nbytes, stream):
+        _check(self.lib, self.lib.b200dp_peer_copy(self.h, seg, peer, byte_off, dst, nbytes, stream), "b200dp_peer_copy")
 
     def gather(self, seg, byte_off, src, nbytes, dst, dst_stride, channel, max_blocks, stream):
         _check(self.lib, self.lib.b200dp_gather(self.h, seg, byte_off, src, nbytes, dst, dst_stride, channel, max_blocks, stream),

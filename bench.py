@@ -795,10 +795,13 @@ def kernel_roofline(acc, model, rt, world, peaks, peak_src):
     for ctas in (16, 32, 64, 148):
         t_copy = clock(lambda _: rt.ctx.pull(group.segment.seg, 0, span, sink.data_ptr(), 0, nbr, 1, native.CH_USER, ctas, st), None)
         by_ctas[ctas] = span / (t_copy * 1e-3) / 1e9
+    t_ce = clock(lambda _: rt.ctx.peer_copy(group.segment.seg, nbr, 0, sink.data_ptr(), span, st), None)
+    by_ctas["copy_engine"] = span / (t_ce * 1e-3) / 1e9
     nvlink_peak = max(by_ctas.values())
-    extra["nvlink_peer_copy"] = {"GBps_per_direction": nvlink_peak, "bytes": span, "GBps_by_ctas": by_ctas,
-                                 "how": "pull_kernel: every rank reads 256 MiB from rank+1's symmetric segment into local HBM, all "
-                                        "ranks at once (each GPU's links carry one stream in and one out); best CTA count, max over ranks"}  # fmt: skip
+    extra["nvlink_peer_copy"] = {"GBps_per_direction": nvlink_peak, "bytes": span, "GBps_by_method": by_ctas,
+                                 "how": "every rank reads 256 MiB from rank+1's symmetric segment into local HBM, all ranks at once "
+                                        "(each GPU's links carry one stream in and one out): pull_kernel with 16/32/64/148 CTAs and a "
+                                        "copy-engine cudaMemcpyAsync over the peer mapping; best method, max over ranks"}  # fmt: skip
     del sink
 
     counters = NvlinkCounters(dev)

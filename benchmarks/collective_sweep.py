@@ -65,6 +65,21 @@ def main():
             if gather_ok:
                 ms = timeit(lambda: rt.ctx.gather(staging.seg, 0, t.data_ptr(), nbytes, out_g.data_ptr(), nbytes, native.CH_USER, blocks, st), nbytes)
                 row[f"gather_b{blocks}_busbw"] = nbytes * ag / (ms * 1e-3) / 1e9
+        # the round-1 sequences the fused kernels replace: pack -> in-place allreduce on staging -> pack out ; pack -> pull
+        def unfused_reduce():
+            rt.ctx.pack([t.data_ptr()], [staging.ptr], [nbytes], rt.bulk_for(nbytes), st)
+            rt.ctx.allreduce_bucket(staging.seg, 0, n, native.F32, 1.0, -1, 0, algo, native.CH_USER, 0, native.NO_STREAM, st)
+            rt.ctx.pack([staging.ptr], [out_r.data_ptr()], [nbytes], rt.bulk_for(nbytes), st)
+
+        def unfused_gather():
+            rt.ctx.pack([t.data_ptr()], [staging.ptr], [nbytes], rt.bulk_for(nbytes), st)
+            rt.ctx.pull(staging.seg, 0, nbytes, out_g.data_ptr(), nbytes, 0, world, native.CH_USER, 0, st)
+
+        ms = timeit(unfused_reduce, nbytes)
+        row["unfused_reduce_busbw"] = nbytes * ar / (ms * 1e-3) / 1e9
+        if gather_ok:
+            ms = timeit(unfused_gather, nbytes)
+            row["unfused_gather_busbw"] = nbytes * ag / (ms * 1e-3) / 1e9
         if nccl:
             ms = timeit(lambda: dist.all_reduce(out_r), nbytes)
             row["nccl_allreduce_busbw"] = nbytes * ar / (ms * 1e-3) / 1e9

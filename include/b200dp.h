@@ -240,6 +240,10 @@ int b200dp_gather(b200dp_ctx* ctx, int seg, size_t byte_off, const void* src, si
 int b200dp_reduce(b200dp_ctx* ctx, int seg, size_t byte_off, const void* src, size_t count, int dtype,
                   double divisor, void* dst, int algo, int channel, int max_blocks, void* stream);
 
+/* Copy-engine read of `nbytes` from rank `peer`'s copy of `seg` into local memory (cudaMemcpyAsync over the peer
+ * mapping): the NVLink yardstick bench.py measures the kernels against.  Not used on the data path. */
+int b200dp_peer_copy(b200dp_ctx* ctx, int seg, int peer, size_t byte_off, void* dst, size_t nbytes, void* stream);
+
 /* ---- K2b: latency path (one launch, one barrier) for messages up to b200dp_push_max_bytes() per rank.
  * Replaces all_gather_into_tensor / all_reduce for small tensors (operations.py:342,871).  The last
  * b200dp_push_area_bytes() bytes of segment `seg` are used as per-CTA, double-buffered windows, so
