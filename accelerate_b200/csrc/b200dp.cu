@@ -128,6 +128,7 @@ constexpr int kMaxSeg = 32;
 constexpr int kStatAreas = B200DP_NUM_CHANNELS + 1;  // one partial area per channel + multi_stats
 constexpr int kEventPool = 64;
 constexpr int kPartialMax = 1280;  // CTAs that may leave a stats partial (>= 8 x 148)
+constexpr int kPipeMaxChunks = 1024;
 
 struct Segment {
   bool used = false;
@@ -153,6 +154,7 @@ struct b200dp_ctx {
   uint32_t* d_ctr = nullptr;      // [NUM_CHANNELS][MAX_BLOCKS]
   Record* d_partial = nullptr;    // [kStatAreas][MAX_BLOCKS]
   uint32_t* d_ticket = nullptr;   // [kStatAreas]
+  uint32_t* d_pipe = nullptr;     // [2][kPipeMaxChunks] hand-off counters of reduce_pipelined_kernel
   int* h_status = nullptr;        // mapped pinned
   int* d_status = nullptr;        // device alias of h_status
   uint32_t* h_small = nullptr;    // mapped pinned [MAX_WORLD * SMALL_MAX/4]
@@ -241,6 +243,8 @@ extern "C" int b200dp_init(int rank, int world, int device, b200dp_ctx** out) {
   RT(cudaMemset(c->d_partial, 0, sizeof(Record) * kStatAreas * kPartialMax));
   RT(cudaMalloc(&c->d_ticket, sizeof(uint32_t) * kStatAreas));
   RT(cudaMemset(c->d_ticket, 0, sizeof(uint32_t) * kStatAreas));
+  RT(cudaMalloc(&c->d_pipe, sizeof(uint32_t) * 2 * kPipeMaxChunks));
+  RT(cudaMemset(c->d_pipe, 0, sizeof(uint32_t) * 2 * kPipeMaxChunks));
   RT(cudaHostAlloc(&c->h_status, 64, cudaHostAllocMapped));
   *c->h_status = 0;
   RT(cudaHostGetDevicePointer(&c->d_status, c->h_status, 0));
@@ -273,6 +277,7 @@ extern "C" int b200dp_finalize(b200dp_ctx* c) {
   cudaFree(c->d_ctr);
   cudaFree(c->d_partial);
   cudaFree(c->d_ticket);
+  cudaFree(c->d_pipe);
   if (c->h_status) cudaFreeHost(c->h_status);
   if (c->h_small) cudaFreeHost(c->h_small);
   cudaGetLastError();
@@ -1179,6 +1184,20 @@ extern "C" int b200dp_gather(b200dp_ctx* c, int seg, size_t byte_off, const void
 }
 
 template <typename T>
+static void launch_pipe_reduce(const PipeReduceArgs& a, int world, bool nvls, int grid, cudaStream_t st) {
+  if (nvls) {
+    reduce_pipelined_kernel<T, 0, true><<<grid, kThreads, 0, st>>>(a);
+    return;
+  }
+  switch (world) {
+    case 2: reduce_pipelined_kernel<T, 2, false><<<grid, kThreads, 0, st>>>(a); break;
+    case 4: reduce_pipelined_kernel<T, 4, false><<<grid, kThreads, 0, st>>>(a); break;
+    case 8: reduce_pipelined_kernel<T, 8, false><<<grid, kThreads, 0, st>>>(a); break;
+    default: reduce_pipelined_kernel<T, 0, false><<<grid, kThreads, 0, st>>>(a); break;
+  }
+}
+
+template <typename T>
 static void launch_reduce(const ReduceArgs& a, int world, bool nvls, int grid, cudaStream_t st) {
   if (nvls) {
     reduce_fused_kernel<T, 0, true><<<grid, kThreads, 0, st>>>(a);
@@ -1217,6 +1236,43 @@ extern "C" int b200dp_reduce(b200dp_ctx* c, int seg, size_t byte_off, const void
     return fail(B200DP_EINVAL, "bad algo %d for b200dp_reduce", algo);
   }
   DeviceGuard g(c->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  // ---- large messages: the pipelined kernel (comm CTAs + copy CTAs, chunk hand-off) ----
+  static const size_t pipe_min = size_t(env_blocks("B200DP_PIPE_MIN_MB", 8)) << 20;
+  static const size_t pipe_chunk = size_t(env_blocks("B200DP_PIPE_CHUNK_MB", 8)) << 20;
+  static const int pipe_on = env_blocks("B200DP_PIPE_REDUCE", 1);
+  if (pipe_on == 1 && count * es >= pipe_min && c->sm_count >= 64) {
+    PipeReduceArgs p;
+    if ((rc = make_barrier(c, channel, &p.bar))) return rc;
+    fill_peers(c, *s, &p.bufs);
+    p.mc = reinterpret_cast<char*>(s->mc_ptr);
+    p.byte_off = byte_off;
+    p.count = count;
+    p.src = src;
+    p.dst = dst;
+    p.divisor = float(divisor);
+    const size_t nvec = (count * es + 15) / 16;
+    size_t chunk_vecs = pipe_chunk / 16;
+    while ((nvec + chunk_vecs - 1) / chunk_vecs > size_t(kPipeMaxChunks)) chunk_vecs *= 2;
+    p.chunk_vecs = chunk_vecs;
+    p.nchunks = int((nvec + chunk_vecs - 1) / chunk_vecs);
+    static const int ncomm_nvls = env_blocks("B200DP_PIPE_COMM_NVLS", 16), ncomm_two = env_blocks("B200DP_PIPE_COMM_TWOSHOT", 32);
+    p.ncomm = nvls ? ncomm_nvls : ncomm_two;
+    const int grid = max_blocks > 0 && max_blocks < c->sm_count ? max_blocks : c->sm_count;
+    if (p.ncomm > grid / 2) p.ncomm = grid / 2;
+    if (p.ncomm < 1) p.ncomm = 1;
+    p.lag = 2;
+    p.staged = c->d_pipe;
+    p.reduced = c->d_pipe + kPipeMaxChunks;
+    RT(cudaMemsetAsync(c->d_pipe, 0, sizeof(uint32_t) * 2 * kPipeMaxChunks, st));
+    switch (dtype) {
+      case B200DP_F32: launch_pipe_reduce<float>(p, c->world, nvls, grid, st); break;
+      case B200DP_BF16: launch_pipe_reduce<__nv_bfloat16>(p, c->world, nvls, grid, st); break;
+      default: launch_pipe_reduce<__half>(p, c->world, nvls, grid, st); break;
+    }
+    KERNEL_OK(c);
+    return B200DP_OK;
+  }
   ReduceArgs a;
   if ((rc = make_barrier(c, channel, &a.bar))) return rc;
   fill_peers(c, *s, &a.bufs);
@@ -1228,7 +1284,6 @@ extern "C" int b200dp_reduce(b200dp_ctx* c, int seg, size_t byte_off, const void
   a.divisor = float(divisor);
   static const int dflt = env_blocks("B200DP_REDUCE_FUSED_BLOCKS", 148);  // the local copy phases want every SM (r02 sweep)
   const int grid = clamp_blocks(c, (count * es + 15) / 16, size_t(kThreads) * 4, max_blocks > 0 ? max_blocks : dflt);
-  cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {
     case B200DP_F32: launch_reduce<float>(a, c->world, nvls, grid, st); break;
     case B200DP_BF16: launch_reduce<__nv_bfloat16>(a, c->world, nvls, grid, st); break;

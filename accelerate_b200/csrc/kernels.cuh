@@ -624,6 +624,220 @@ __global__ void __launch_bounds__(kThreads, 1) reduce_fused_kernel(const ReduceA
 }
 
 // ------------------------------------------------------------------------------------------------
+// K1d: pipelined out-of-place allreduce for large tensors in ordinary torch memory.  One launch, two kinds of CTA:
+//   * COMM CTAs (the first `ncomm`, the same indices on every rank) own the NVLink side: per chunk they wait until the
+//     local copy CTAs staged it, meet their peers at a flag barrier, reduce this rank's share of the chunk over all
+//     ranks' staged copies (NVLS multimem, or two-shot peer loads / stores) and, after a second barrier, hand the
+//     chunk back;
+//   * COPY CTAs (all the others) own the HBM side: stage chunk c (input -> symmetric staging), then copy a finished
+//     chunk (staging -> output, dividing on the way for "mean"), a few chunks behind.
+// Chunk c+1 is being staged and chunk c-1 copied out while chunk c crosses the switch, so the time is
+// max(NVLink, HBM) instead of their sum — what the three-launch sequence (pack, in-place allreduce, pack) cannot do.
+// NVLS streams best with few CTAs, HBM copies want many: the split gives each side what it needs.
+// Local hand-off = two counters per chunk in device memory (zeroed by the host before the launch).
+// ------------------------------------------------------------------------------------------------
+struct PipeReduceArgs {
+  BarrierCtx bar;
+  Peers bufs;          // staging segment bases
+  char* mc;            // multicast VA of the staging segment (NVLS) or nullptr
+  size_t byte_off;     // staging window (16-byte aligned)
+  size_t count;        // elements
+  const void* src;
+  void* dst;
+  float divisor;
+  uint32_t* staged;    // [nchunks] arrivals of copy CTAs (local)
+  uint32_t* reduced;   // [nchunks] arrivals of comm CTAs (local)
+  size_t chunk_vecs;   // 16-byte vectors per chunk
+  int nchunks;
+  int ncomm;           // comm CTAs; gridDim.x - ncomm copy CTAs
+  int lag;             // copy CTAs copy out chunk c - lag after staging chunk c
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// all threads of the CTA call it; returns when *p >= want (or the context timed out)
+__device__ __forceinline__ void wait_counter(const BarrierCtx& b, const uint32_t* p, uint32_t want) {
+  if (threadIdx.x == 0) {
+    unsigned long long t0 = 0;
+    uint32_t spins = 0;
+    while (ld_acquire_gpu(p) < want) {
+      if ((++spins & 0x3ff) == 0) {
+        unsigned long long now = globaltimer_ns();
+        if (t0 == 0) t0 = now;
+        if (now - t0 > b.timeout_ns || *reinterpret_cast<volatile int*>(b.status) != 0) {
+          *reinterpret_cast<volatile int*>(b.status) = B200DP_ETIMEOUT;
+          __threadfence_system();
+          break;
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ void signal_counter(uint32_t* p) {
+  __syncthreads();  // every thread's stores of this phase are ordered before the release below
+  if (threadIdx.x == 0) red_release_gpu_add(p, 1u);
+}
+
+template <typename T, int W, bool NVLS>
+__global__ void __launch_bounds__(kThreads, 1) reduce_pipelined_kernel(const PipeReduceArgs a) {
+  constexpr int N = Vec16<T>::N;
+  const BarrierCtx& b = a.bar;
+  const int world = b.world;
+  const size_t nbytes = a.count * sizeof(T);
+  const size_t nvec = (nbytes + 15) >> 4;
+  char* mine = reinterpret_cast<char*>(a.bufs.p[b.rank]) + a.byte_off;
+
+  if (int(blockIdx.x) < a.ncomm) {
+    // ------------------------------------------------------------------ COMM role
+    // two groups (even / odd CTA index) take the even / odd chunks: while one group sits in its flag barriers the
+    // other one streams, so the links never idle for a barrier round trip
+    const uint32_t base = barrier_seq_begin(b);
+    const uint32_t ncopy = gridDim.x - a.ncomm;
+    const int ngroups = a.ncomm >= 2 ? 2 : 1;
+    const int group = int(blockIdx.x) % ngroups, gidx = int(blockIdx.x) / ngroups;
+    const int gsize = (a.ncomm - group + ngroups - 1) / ngroups;
+    uint32_t k = 0;  // chunks this CTA has handled
+    for (int c = group; c < a.nchunks; c += ngroups, ++k) {
+      const size_t clo = size_t(c) * a.chunk_vecs;
+      const size_t chi = (clo + a.chunk_vecs < nvec) ? clo + a.chunk_vecs : nvec;
+      wait_counter(b, a.staged + c, ncopy);       // my copy CTAs staged chunk c
+      cross_rank_barrier(b, base + 1 + 2 * k);    // ... and so did comm CTA `blockIdx.x` of every peer
+      // this rank's share of the chunk, then this comm CTA's share of that
+      const size_t per_rank = (chi - clo + world - 1) / world;
+      size_t rlo = clo + size_t(b.rank) * per_rank, rhi = rlo + per_rank;
+      if (rlo > chi) rlo = chi;
+      if (rhi > chi) rhi = chi;
+      const size_t per_cta = (rhi - rlo + gsize - 1) / gsize;
+      size_t slo = rlo + size_t(gidx) * per_cta, shi = slo + per_cta;
+      if (slo > rhi) slo = rhi;
+      if (shi > rhi) shi = rhi;
+      if constexpr (NVLS) {
+        char* mcb = a.mc + a.byte_off;
+        constexpr int U = 4;
+        for (size_t i = slo + threadIdx.x; i < shi; i += size_t(U) * blockDim.x) {
+          uint4 v[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const size_t j = i + size_t(u) * blockDim.x;
+            if (j < shi) v[u] = MultimemOps<T>::ld_reduce(mcb + j * 16);
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const size_t j = i + size_t(u) * blockDim.x;
+            if (j < shi) multimem_st16(mcb + j * 16, v[u]);
+          }
+        }
+      } else {
+        constexpr int U = (W == 0 || W >= 5) ? 2 : 4;
+        for (size_t i = slo + threadIdx.x; i < shi; i += size_t(U) * blockDim.x) {
+          float acc[U][N];
+          bool ok[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const size_t j = i + size_t(u) * blockDim.x;
+            ok[u] = j < shi;
+            if (!ok[u]) continue;
+            if constexpr (W > 0) {
+              uint4 v[W];
+#pragma unroll
+              for (int r = 0; r < W; ++r) v[r] = ld_stream16(reinterpret_cast<const char*>(a.bufs.p[r]) + a.byte_off + j * 16);
+              Vec16<T>::unpack(v[0], acc[u]);
+#pragma unroll
+              for (int r = 1; r < W; ++r) {
+                float x[N];
+                Vec16<T>::unpack(v[r], x);
+#pragma unroll
+                for (int k = 0; k < N; ++k) acc[u][k] = __fadd_rn(acc[u][k], x[k]);
+              }
+            } else {
+              Vec16<T>::unpack(ld_stream16(reinterpret_cast<const char*>(a.bufs.p[0]) + a.byte_off + j * 16), acc[u]);
+              for (int r = 1; r < world; ++r) {
+                float x[N];
+                Vec16<T>::unpack(ld_stream16(reinterpret_cast<const char*>(a.bufs.p[r]) + a.byte_off + j * 16), x);
+#pragma unroll
+                for (int k = 0; k < N; ++k) acc[u][k] = __fadd_rn(acc[u][k], x[k]);
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            if (!ok[u]) continue;
+            const size_t j = i + size_t(u) * blockDim.x;
+            const uint4 o = Vec16<T>::pack(acc[u]);
+            for (int r = 0; r < world; ++r) st_stream16(reinterpret_cast<char*>(a.bufs.p[r]) + a.byte_off + j * 16, o);
+          }
+        }
+      }
+      cross_rank_barrier(b, base + 2 + 2 * k);  // every owner's share of chunk c has landed in my staging
+      if (threadIdx.x == 0) red_release_gpu_add(a.reduced + c, 1u);
+    }
+    barrier_seq_end(b, base, 2 * k);  // the same k on every rank: it depends only on (blockIdx, nchunks, ncomm)
+    return;
+  }
+
+  // -------------------------------------------------------------------- COPY role
+  const int me = int(blockIdx.x) - a.ncomm, ncopy = int(gridDim.x) - a.ncomm;
+  const size_t tid = threadIdx.x, nthreads = blockDim.x;
+  auto my_span = [&](int c, size_t& blo, size_t& bhi) {
+    const size_t clo = size_t(c) * a.chunk_vecs;
+    const size_t chi = (clo + a.chunk_vecs < nvec) ? clo + a.chunk_vecs : nvec;
+    const size_t per = (chi - clo + ncopy - 1) / ncopy;
+    size_t vlo = clo + size_t(me) * per, vhi = vlo + per;
+    if (vlo > chi) vlo = chi;
+    if (vhi > chi) vhi = chi;
+    blo = vlo * 16;
+    bhi = vhi * 16;
+    if (blo > nbytes) blo = nbytes;
+    if (bhi > nbytes) bhi = nbytes;
+  };
+  const int ngroups_c = a.ncomm >= 2 ? 2 : 1;
+  auto copy_out = [&](int c) {
+    const int g = c % ngroups_c;
+    wait_counter(b, a.reduced + c, uint32_t((a.ncomm - g + ngroups_c - 1) / ngroups_c));
+    size_t blo, bhi;
+    my_span(c, blo, bhi);
+    char* out = reinterpret_cast<char*>(a.dst);
+    if (a.divisor == 1.0f) {
+      copy_span(out + blo, mine + blo, bhi - blo, tid, nthreads);
+    } else if ((reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+      const T* sp = reinterpret_cast<const T*>(mine);
+      T* op = reinterpret_cast<T*>(out);
+      for (size_t j = blo / 16 + tid; j < (bhi + 15) / 16; j += nthreads) {
+        if ((j + 1) * N <= a.count) {
+          float f[N];
+          Vec16<T>::unpack(ld_stream16(mine + j * 16), f);
+#pragma unroll
+          for (int q = 0; q < N; ++q) f[q] = __fdiv_rn(f[q], a.divisor);
+          *reinterpret_cast<uint4*>(out + j * 16) = Vec16<T>::pack(f);
+        } else {
+          for (size_t e = j * N; e < a.count; ++e) op[e] = from_float<T>(__fdiv_rn(to_float<T>(sp[e]), a.divisor));
+        }
+      }
+    } else {
+      const T* sp = reinterpret_cast<const T*>(mine);
+      T* op = reinterpret_cast<T*>(out);
+      for (size_t e = blo / sizeof(T) + tid; e < bhi / sizeof(T); e += nthreads)
+        op[e] = from_float<T>(__fdiv_rn(to_float<T>(sp[e]), a.divisor));
+    }
+  };
+  for (int c = 0; c < a.nchunks; ++c) {
+    size_t blo, bhi;
+    my_span(c, blo, bhi);
+    copy_any(mine + blo, reinterpret_cast<const char*>(a.src) + blo, bhi - blo, tid, nthreads);
+    signal_counter(a.staged + c);
+    if (c >= a.lag) copy_out(c - a.lag);
+  }
+  for (int c = (a.nchunks > a.lag ? a.nchunks - a.lag : 0); c < a.nchunks; ++c) copy_out(c);
+}
+
+// ------------------------------------------------------------------------------------------------
 // K2b: latency path for small messages: ONE launch, ONE barrier.  Every rank pushes its data into a
 // fixed window of every peer's staging segment (posted NVLink stores), then reads all N windows
 // locally and either concatenates (gather) or sums in rank order (reduce).  Windows are private to a

@@ -85,11 +85,14 @@ def test_three_ranks_two_shot_bit_exact():
     assert out.count("ALLREDUCE_CHECK_OK") == 3, out[-3000:]
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_large_gather_and_reduce_fused_kernels(world):
-    """accelerator.gather / reduce above the latency path: one fused launch per staging window (b200dp_gather /
-    b200dp_reduce), ragged sizes, odd source offsets, all float dtypes, mean, > window (32 MiB staging forces chunking)."""
-    out = run_distributed("dist_collectives_large.py", world, env=dict(ENV, B200DP_STAGING_MB="32"), timeout=900)
+@pytest.mark.parametrize("world,pipe_chunk_mb,fused", [(2, "1", "1"), (4, "8", "1"), (2, "8", "0")])
+def test_large_gather_and_reduce_fused_kernels(world, pipe_chunk_mb, fused):
+    """accelerator.gather / reduce above the latency path: one launch per staging window — b200dp_gather (stage + pull),
+    b200dp_reduce (fused below 8 MiB, the pipelined comm-CTA / copy-CTA kernel above; 1 MiB chunks force a dozen
+    hand-offs per call) — ragged sizes, odd source offsets, all float dtypes, mean, messages larger than the window
+    (32 MiB staging forces several launches).  fused=0: the round-1 three-launch sequences the sweep compares against."""
+    env = dict(ENV, B200DP_STAGING_MB="32", B200DP_PIPE_CHUNK_MB=pipe_chunk_mb, B200DP_FUSED_GATHER=fused, B200DP_FUSED_REDUCE=fused)
+    out = run_distributed("dist_collectives_large.py", world, env=env, timeout=900)
     assert out.count("COLLECTIVES_LARGE_OK") == world, out[-3000:]
 
 
