@@ -1239,9 +1239,19 @@ extern "C" int b200dp_reduce(b200dp_ctx* c, int seg, size_t byte_off, const void
   cudaStream_t st = (cudaStream_t)stream;
   // ---- large messages: the pipelined kernel (comm CTAs + copy CTAs, chunk hand-off) ----
   static const size_t pipe_min = size_t(env_blocks("B200DP_PIPE_MIN_MB", 8)) << 20;
-  static const size_t pipe_chunk = size_t(env_blocks("B200DP_PIPE_CHUNK_MB", 8)) << 20;
+  // chunk = 1/8 of the message clamped to [4, 16] MiB unless B200DP_PIPE_CHUNK_MB pins it: per-chunk cost (one flag
+  // barrier + the multimem ramp, ~4 us) against pipeline depth (profiles/r02_collective_sweep_n4_*.json)
+  static const size_t pipe_chunk_env = size_t(env_blocks("B200DP_PIPE_CHUNK_MB", 0)) << 20;
+  size_t pipe_chunk = pipe_chunk_env;
+  if (pipe_chunk == 0) {
+    pipe_chunk = (count * es / 8) >> 20 << 20;
+    if (pipe_chunk < (size_t(4) << 20)) pipe_chunk = size_t(4) << 20;
+    if (pipe_chunk > (size_t(16) << 20)) pipe_chunk = size_t(16) << 20;
+  }
   static const int pipe_on = env_blocks("B200DP_PIPE_REDUCE", 1);
-  if (pipe_on == 1 && count * es >= pipe_min && c->sm_count >= 64) {
+  // (two-shot worlds keep the fused kernel: with plain peer loads the per-chunk hand-off costs more than it hides)
+  // (B200DP_PIPE_REDUCE=2 forces it for any algorithm: tests exercise the two-shot instantiation that way)
+  if (((pipe_on == 1 && nvls) || pipe_on == 2) && count * es >= pipe_min && c->sm_count >= 64) {
     PipeReduceArgs p;
     if ((rc = make_barrier(c, channel, &p.bar))) return rc;
     fill_peers(c, *s, &p.bufs);

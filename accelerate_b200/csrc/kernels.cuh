@@ -704,11 +704,17 @@ __global__ void __launch_bounds__(kThreads, 1) reduce_pipelined_kernel(const Pip
     const int group = int(blockIdx.x) % ngroups, gidx = int(blockIdx.x) / ngroups;
     const int gsize = (a.ncomm - group + ngroups - 1) / ngroups;
     uint32_t k = 0;  // chunks this CTA has handled
+    int prev = -1;
     for (int c = group; c < a.nchunks; c += ngroups, ++k) {
       const size_t clo = size_t(c) * a.chunk_vecs;
       const size_t chi = (clo + a.chunk_vecs < nvec) ? clo + a.chunk_vecs : nvec;
-      wait_counter(b, a.staged + c, ncopy);       // my copy CTAs staged chunk c
-      cross_rank_barrier(b, base + 1 + 2 * k);    // ... and so did comm CTA `blockIdx.x` of every peer
+      wait_counter(b, a.staged + c, ncopy);  // my copy CTAs staged chunk c
+      // ONE barrier per chunk.  A peer CTA that arrives here has (a) staged chunk c and (b) finished storing its share of
+      // this group's previous chunk into my staging (its stores precede its flag release in program order): the
+      // "results have landed" barrier of chunk `prev` and the "inputs are staged" barrier of chunk c are the same one.
+      cross_rank_barrier(b, base + 1 + k);
+      if (prev >= 0 && threadIdx.x == 0) red_release_gpu_add(a.reduced + prev, 1u);
+      prev = c;
       // this rank's share of the chunk, then this comm CTA's share of that
       const size_t per_rank = (chi - clo + world - 1) / world;
       size_t rlo = clo + size_t(b.rank) * per_rank, rhi = rlo + per_rank;
@@ -775,10 +781,13 @@ __global__ void __launch_bounds__(kThreads, 1) reduce_pipelined_kernel(const Pip
           }
         }
       }
-      cross_rank_barrier(b, base + 2 + 2 * k);  // every owner's share of chunk c has landed in my staging
-      if (threadIdx.x == 0) red_release_gpu_add(a.reduced + c, 1u);
     }
-    barrier_seq_end(b, base, 2 * k);  // the same k on every rank: it depends only on (blockIdx, nchunks, ncomm)
+    if (prev >= 0) {
+      cross_rank_barrier(b, base + 1 + k);  // closing: every owner's share of the last chunk has landed in my staging
+      if (threadIdx.x == 0) red_release_gpu_add(a.reduced + prev, 1u);
+      ++k;
+    }
+    barrier_seq_end(b, base, k);  // the same k on every rank: it depends only on (blockIdx, nchunks, ncomm)
     return;
   }
 
