@@ -59,7 +59,10 @@ _KEEP_STAGED = os.environ.get("B200DP_KEEP_STAGED", "0") == "1"
 _SAME_STREAM = os.environ.get("B200DP_SAME_STREAM", "0") == "1"
 _PACK_ON_COMM = os.environ.get("B200DP_PACK_ON_COMM", "1") == "1"
 _NVLS_MIN_WORLD = int(os.environ.get("B200DP_NVLS_MIN_WORLD", "4"))
-_NVLS_BLOCKS = int(os.environ.get("B200DP_NVLS_BLOCKS", "16"))
+# 8 CTAs: same bus bandwidth as 16 on 25 MiB buckets (665 vs 657 GB/s at 8 GPUs) with half the SMs taken from the
+# backward kernels the reduction overlaps with: +0.55 % samples/s at 8 GPUs in r01 and again in r02
+# (profiles/r02_bench_n8.json vs r02_bench_n8_nvls_8ctas.json)
+_NVLS_BLOCKS = int(os.environ.get("B200DP_NVLS_BLOCKS", "8"))
 _TWOSHOT_BLOCKS = int(os.environ.get("B200DP_TWOSHOT_BLOCKS", "32"))
 
 
