@@ -27,6 +27,16 @@ ONESHOT_MAX_BYTES = 512 * 1024
 # (pack -> pull / in-place allreduce -> pack) that the fused kernels are measured against (benchmarks/collective_sweep.py).
 FUSED_GATHER = os.environ.get("B200DP_FUSED_GATHER", "1") != "0"
 FUSED_REDUCE = os.environ.get("B200DP_FUSED_REDUCE", "1") != "0"
+# gather: below this many bytes per rank the two-launch sequence (pack with the whole chip, then pull) is still a few
+# per cent faster than the fused kernel, above it the fused kernel wins (r02 sweeps: 2 GPUs 430 vs 409 GB/s at 64 MiB,
+# 8 GPUs 614 vs 603 at 256 MiB but 568 vs 580 at 64 MiB).  B200DP_FUSED_GATHER_MIN_MB overrides (0 = always fused).
+_FUSED_GATHER_MIN_MB = os.environ.get("B200DP_FUSED_GATHER_MIN_MB")
+
+
+def _fused_gather_min(world: int) -> int:
+    if _FUSED_GATHER_MIN_MB is not None:
+        return int(_FUSED_GATHER_MIN_MB) << 20
+    return (32 if world <= 2 else 128) << 20
 
 
 def _bulk_capacity(rt, staging) -> int:
@@ -69,9 +79,10 @@ def all_gather(t: torch.Tensor) -> torch.Tensor:
     cap = _bulk_capacity(rt, staging)
     src, dst = t.data_ptr(), out.data_ptr()
     done = 0
+    fused = FUSED_GATHER and nbytes >= _fused_gather_min(world)
     while done < nbytes:
         n = min(cap, nbytes - done)
-        if FUSED_GATHER:
+        if fused:
             rt.ctx.gather(staging.seg, 0, src + done, n, dst + done, nbytes, native.CH_USER, 0, st)
         else:
             rt.ctx.pack([src + done], [staging.ptr], [n], rt.bulk_for(n), st)
