@@ -69,3 +69,10 @@ def test_join_uneven_inputs_matches_torch_ddp(world, find_unused):
     shadow the collectives; parameters after every step and the final synced model equal torch DDP's."""
     out = run_distributed("dist_join.py", world, timeout=300, env={"JOIN_FIND_UNUSED": find_unused})
     assert out.count("JOIN_OK") == world, out[-3000:]
+
+
+def test_frozen_parameters_and_buffers_are_synchronised():
+    """every parameter — frozen ones too — and every buffer equals rank 0's after prepare (torch's
+    `_sync_module_states`), and LocalSGD averages the frozen ones like the reference does."""
+    out = run_distributed("dist_frozen.py", 2, timeout=300)
+    assert out.count("FROZEN_OK") == 2, out[-3000:]
