@@ -49,8 +49,9 @@ class FusedAdamPlan:
     and writes p, m, v.  Two layouts:
 
     * *buffer* (multi-GPU): the gradients are views of one reducer's fusion buffer; the moments live in two flat
-      buffers with the same layout, the pointer table is built once.  With ``B200DP_DEFER_CLIP=1`` the pending
-      clip / unscale multiplier is applied on the fly, so the separate multiply pass over the gradients disappears.
+      buffers with the same layout, the pointer table is built once.  The pending clip / unscale multiplier
+      (``lazy_grad.py``, on by default) is applied on the fly, so the separate multiply pass over the gradients
+      disappears; under a ``GradScaler`` the kernel also reads the found-inf flag on the device.
     * *loose* (one process, no reducer): the gradients are whatever tensors autograd left in ``param.grad``; their
       pointers are collected per step, the moments still live in two flat buffers.
 

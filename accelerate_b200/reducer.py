@@ -59,10 +59,12 @@ _KEEP_STAGED = os.environ.get("B200DP_KEEP_STAGED", "0") == "1"
 _SAME_STREAM = os.environ.get("B200DP_SAME_STREAM", "0") == "1"
 _PACK_ON_COMM = os.environ.get("B200DP_PACK_ON_COMM", "1") == "1"
 _NVLS_MIN_WORLD = int(os.environ.get("B200DP_NVLS_MIN_WORLD", "4"))
-# 8 CTAs: same bus bandwidth as 16 on 25 MiB buckets (665 vs 657 GB/s at 8 GPUs) with half the SMs taken from the
-# backward kernels the reduction overlaps with: +0.55 % samples/s at 8 GPUs in r01 and again in r02
-# (profiles/r02_bench_n8.json vs r02_bench_n8_nvls_8ctas.json)
-_NVLS_BLOCKS = int(os.environ.get("B200DP_NVLS_BLOCKS", "8"))
+# NVLS CTAs per bucket kernel, 0 = by world size: a rank streams S/N of every bucket through its SMs, so the CTA count
+# that saturates the links shrinks with N.  8 GPUs: 8 CTAs give the same bus bandwidth as 16 on 25 MiB buckets (665 vs
+# 657 GB/s) with half the SMs taken from the backward kernels (+0.55 % samples/s in r01 and again in r02:
+# profiles/r02_bench_n8_nvls_16ctas.json vs _8ctas.json); 4 GPUs: 8 CTAs lose (441 vs 543 GB/s, 1.42 GB launch 529 vs
+# 684: profiles/r02_bench_n4_nvls_8ctas.json vs r02_bench_n4.json), so 16 there.
+_NVLS_BLOCKS = int(os.environ.get("B200DP_NVLS_BLOCKS", "0"))
 _TWOSHOT_BLOCKS = int(os.environ.get("B200DP_TWOSHOT_BLOCKS", "32"))
 
 
@@ -500,7 +502,9 @@ class GradReducer:
     def blocks_for(self, algo: int) -> int:
         if self.max_blocks > 0:
             return self.max_blocks
-        return _NVLS_BLOCKS if algo == native.ALGO_NVLS else _TWOSHOT_BLOCKS
+        if algo == native.ALGO_NVLS:
+            return _NVLS_BLOCKS if _NVLS_BLOCKS > 0 else (8 if self.world >= 8 else 16)
+        return _TWOSHOT_BLOCKS
 
     def _reduce_bucket_wire(self, b: GradBucket, cs: int):
         """Half-precision wire (the reference's fp16/bf16 compress hooks): cast+pre-divide the bucket into the
