@@ -1237,6 +1237,30 @@ extern "C" int b200dp_reduce(b200dp_ctx* c, int seg, size_t byte_off, const void
   }
   DeviceGuard g(c->device);
   cudaStream_t st = (cudaStream_t)stream;
+  // ---- two ranks: one-shot by push (no staging copy, no copy-out) ----
+  static const int push2_on = env_blocks("B200DP_PUSH2", 1);
+  static const size_t push2_min = size_t(env_blocks("B200DP_PUSH2_MIN_MB", 4)) << 20;
+  if (push2_on == 1 && c->world == 2 && !nvls && count * es >= push2_min && (count * es) % 16 == 0 &&
+      ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+    Push2Args p;
+    if ((rc = make_barrier(c, channel, &p.bar))) return rc;
+    fill_peers(c, *s, &p.bufs);
+    p.byte_off = byte_off;
+    p.nvec = count * es / 16;
+    p.src = reinterpret_cast<const char*>(src);
+    p.dst = reinterpret_cast<char*>(dst);
+    p.divisor = float(divisor);
+    static const size_t round_kb = size_t(env_blocks("B200DP_PUSH2_ROUND_KB", 128));
+    p.round_vecs = round_kb * 1024 / 16;
+    const int grid = max_blocks > 0 && max_blocks < c->sm_count ? max_blocks : c->sm_count;
+    switch (dtype) {
+      case B200DP_F32: reduce_push2_kernel<float><<<grid, kThreads, 0, st>>>(p); break;
+      case B200DP_BF16: reduce_push2_kernel<__nv_bfloat16><<<grid, kThreads, 0, st>>>(p); break;
+      default: reduce_push2_kernel<__half><<<grid, kThreads, 0, st>>>(p); break;
+    }
+    KERNEL_OK(c);
+    return B200DP_OK;
+  }
   // ---- large messages: the pipelined kernel (comm CTAs + copy CTAs, chunk hand-off) ----
   static const size_t pipe_min = size_t(env_blocks("B200DP_PIPE_MIN_MB", 8)) << 20;
   // chunk = 1/8 of the message clamped to [4, 16] MiB unless B200DP_PIPE_CHUNK_MB pins it: per-chunk cost (one flag

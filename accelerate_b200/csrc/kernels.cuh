@@ -847,6 +847,100 @@ __global__ void __launch_bounds__(kThreads, 1) reduce_pipelined_kernel(const Pip
 }
 
 // ------------------------------------------------------------------------------------------------
+// K1e: two-rank out-of-place allreduce by PUSH.  With two ranks a one-shot exchange moves exactly as many bytes over
+// NVLink as the two-shot (S per direction) and needs no staging copy and no copy-out: every CTA pushes its portion of the
+// local input straight into the PEER's window (posted NVLink stores), round by round, and — one flag barrier per round,
+// the next round's push already in flight — adds what the peer pushed to its own input in rank order (x_0 + x_1, fp32
+// accumulate, one rounding) and writes the output.  HBM: read S (push) + read 2S + write S (+ S incoming).
+// Preconditions (checked by the host): world == 2, src / dst 16-byte aligned, byte count a multiple of 16.
+// ------------------------------------------------------------------------------------------------
+struct Push2Args {
+  BarrierCtx bar;
+  Peers bufs;          // staging segment bases
+  size_t byte_off;     // staging window (16-byte aligned)
+  size_t nvec;         // 16-byte vectors
+  const char* src;
+  char* dst;
+  float divisor;
+  size_t round_vecs;   // vectors per CTA per round
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 1) reduce_push2_kernel(const Push2Args a) {
+  constexpr int N = Vec16<T>::N;
+  const BarrierCtx& b = a.bar;
+  const uint32_t base = barrier_seq_begin(b);
+  const int peer = 1 - b.rank;
+  const size_t per = (a.nvec + gridDim.x - 1) / gridDim.x;
+  size_t vlo = size_t(blockIdx.x) * per, vhi = vlo + per;
+  if (vlo > a.nvec) vlo = a.nvec;
+  if (vhi > a.nvec) vhi = a.nvec;
+  // the number of rounds must be the same for CTA b on both ranks: it depends only on (nvec, grid, round size)
+  const uint32_t rounds = uint32_t((per + a.round_vecs - 1) / a.round_vecs);
+  char* peer_win = reinterpret_cast<char*>(a.bufs.p[peer]) + a.byte_off;
+  const char* my_win = reinterpret_cast<const char*>(a.bufs.p[b.rank]) + a.byte_off;
+  constexpr int U = 4;
+  auto push = [&](uint32_t r) {
+    size_t lo = vlo + size_t(r) * a.round_vecs, hi = lo + a.round_vecs;
+    if (lo > vhi) lo = vhi;
+    if (hi > vhi) hi = vhi;
+    for (size_t i = lo + threadIdx.x; i < hi; i += size_t(U) * blockDim.x) {
+      uint4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const size_t j = i + size_t(u) * blockDim.x;
+        if (j < hi) v[u] = ld_stream16(a.src + j * 16);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const size_t j = i + size_t(u) * blockDim.x;
+        if (j < hi) st_stream16(peer_win + j * 16, v[u]);
+      }
+    }
+  };
+  if (rounds > 0) push(0);
+  for (uint32_t r = 0; r < rounds; ++r) {
+    if (r + 1 < rounds) push(r + 1);     // keep the link busy while waiting for the peer's round r
+    cross_rank_barrier(b, base + 1 + r);  // the peer's rounds <= r have landed in my window
+    size_t lo = vlo + size_t(r) * a.round_vecs, hi = lo + a.round_vecs;
+    if (lo > vhi) lo = vhi;
+    if (hi > vhi) hi = vhi;
+    for (size_t i = lo + threadIdx.x; i < hi; i += size_t(U) * blockDim.x) {
+      uint4 x[U], y[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const size_t j = i + size_t(u) * blockDim.x;
+        if (j < hi) {
+          x[u] = ld_stream16(a.src + j * 16);
+          y[u] = ld_stream16(my_win + j * 16);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const size_t j = i + size_t(u) * blockDim.x;
+        if (j >= hi) continue;
+        float f0[N], f1[N];
+        Vec16<T>::unpack(b.rank == 0 ? x[u] : y[u], f0);  // rank order: x_0 first
+        Vec16<T>::unpack(b.rank == 0 ? y[u] : x[u], f1);
+#pragma unroll
+        for (int k = 0; k < N; ++k) f0[k] = __fadd_rn(f0[k], f1[k]);
+        uint4 o = Vec16<T>::pack(f0);
+        if (a.divisor != 1.0f) {
+          Vec16<T>::unpack(o, f0);
+#pragma unroll
+          for (int k = 0; k < N; ++k) f0[k] = __fdiv_rn(f0[k], a.divisor);
+          o = Vec16<T>::pack(f0);
+        }
+        *reinterpret_cast<uint4*>(a.dst + j * 16) = o;
+      }
+    }
+  }
+  // the peer must be done reading its window before my next call pushes into it again
+  cross_rank_barrier(b, base + 1 + rounds);
+  barrier_seq_end(b, base, rounds + 1);
+}
+
+// ------------------------------------------------------------------------------------------------
 // K2b: latency path for small messages: ONE launch, ONE barrier.  Every rank pushes its data into a
 // fixed window of every peer's staging segment (posted NVLink stores), then reads all N windows
 // locally and either concatenates (gather) or sums in rank order (reduce).  Windows are private to a

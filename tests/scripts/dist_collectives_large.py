@@ -22,7 +22,9 @@ def main():
     rt = PartialState().runtime
     staging = rt.ensure_staging()
     nvls = bool(staging.multicast and world >= 4)
-    sizes = [(1 << 20) + 3, 3 * (1 << 20) + 17, 5 * (1 << 20) + 1]  # elements; the last one exceeds a 16 MiB window in fp32
+    # elements: ragged sizes (fused / pipelined kernels; the third exceeds a 16 MiB window in fp32) and 16-byte-exact ones
+    # (two ranks: the push kernel b200dp_reduce uses for aligned tensors; the last one needs two windows)
+    sizes = [(1 << 20) + 3, 3 * (1 << 20) + 17, 5 * (1 << 20) + 1, 3 * (1 << 20), 6 * (1 << 20)]
     for dtype in (torch.float32, torch.bfloat16, torch.float16):
         for numel in sizes:
             g = torch.Generator().manual_seed(7919 * rank + numel % 1009)

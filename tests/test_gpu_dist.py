@@ -93,7 +93,8 @@ def test_large_gather_and_reduce_fused_kernels(world, pipe_chunk_mb, fused):
     (32 MiB staging forces several launches).  fused=0: the round-1 three-launch sequences the sweep compares against."""
     env = dict(ENV, B200DP_STAGING_MB="32", B200DP_PIPE_CHUNK_MB=pipe_chunk_mb, B200DP_FUSED_GATHER=fused, B200DP_FUSED_REDUCE=fused,
                B200DP_PIPE_REDUCE="2" if pipe_chunk_mb == "1" else "1",  # "2": the pipelined kernel for two-shot worlds too
-               B200DP_FUSED_GATHER_MIN_MB="0")  # the fused gather kernel at every size above the latency path
+               B200DP_FUSED_GATHER_MIN_MB="0",  # the fused gather kernel at every size above the latency path
+               B200DP_PUSH2_ROUND_KB="16" if pipe_chunk_mb == "1" else "128")  # two ranks: several push rounds per CTA
     out = run_distributed("dist_collectives_large.py", world, env=env, timeout=900)
     assert out.count("COLLECTIVES_LARGE_OK") == world, out[-3000:]
 
