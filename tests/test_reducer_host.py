@@ -170,3 +170,54 @@ def test_user_comm_hook_protocol_single_process():
     half = B200DataParallel(small_model())
     half.register_comm_hook(None, default_hooks.bf16_compress_hook)
     assert half.reducer.wire_dtype == torch.bfloat16 and half.reducer.user_hook is None
+
+
+class _Switchable(torch.nn.Module):
+    """Two branches applied in an order chosen per call: the gradient-ready order inside a bucket flips with it."""
+
+    def __init__(self):
+        super().__init__()
+        torch.manual_seed(1)
+        self.a = torch.nn.Linear(6, 6)
+        self.b = torch.nn.Linear(6, 6)
+        self.c = torch.nn.Linear(6, 64)  # large enough to fill a bucket of its own: a and b then share the next one
+        self.order = "ab"
+
+    def forward(self, x):
+        first, second = (self.a, self.b) if self.order == "ab" else (self.b, self.a)
+        return self.c(torch.tanh(second(torch.tanh(first(x)))))
+
+
+def test_fast_hooks_learn_the_firing_order_and_survive_a_change():
+    """Round-2 fast hooks: per bucket only the parameter that fired last in the previous iteration runs Python, every other
+    hook is `list.append`.  When the order changes, the bucket must still be reduced exactly once per backward with all of
+    its gradients final (late, at a later trigger or at the end of backward), and the new order is learned."""
+    import copy
+
+    ddp = B200DataParallel(_Switchable(), bucket_cap_mb=0.0003)  # ~300-byte buckets: [c.bias, c.weight], [b.*, a.*]
+    ref = copy.deepcopy(ddp.module)
+    red = ddp.reducer
+    assert red._fast and [len(b.params) for b in red.buckets] == [2, 4]
+    g = torch.Generator().manual_seed(0)
+    relearned = 0
+    for it, order in enumerate(["ab", "ab", "ba", "ba", "ab", "ba", "ba"]):
+        ddp.module.order = ref.order = order
+        x = torch.randn(5, 6, generator=g)
+        triggers_before = [b.trigger for b in red.buckets]
+        for m in (ddp, ref):
+            m.zero_grad(set_to_none=(it % 2 == 0))
+            m(x).square().mean().backward()
+        assert red.num_reductions == it + 1
+        for p, q in zip(ddp.module.parameters(), ref.parameters()):
+            assert torch.equal(p.grad, q.grad), (it, order)
+        for b in red.buckets:  # gradients live in the fusion buffer afterwards
+            for p, ptr in zip(b.params, b.ptrs):
+                assert p.grad.data_ptr() == ptr
+        relearned += sum(t != b.trigger for t, b in zip(triggers_before, red.buckets))
+    assert relearned >= 1, "flipping the order must have moved at least one bucket's trigger"
+    # a backward under no_sync leaves the reducer idle and the bookkeeping clean
+    with ddp.no_sync():
+        ddp(x).square().mean().backward()
+    assert red.num_reductions == 7
+    ddp(x).square().mean().backward()
+    assert red.num_reductions == 8
