@@ -367,7 +367,7 @@ class GradReducer:
         per-parameter Python hook does one by one) and mark the bucket ready."""
         n = len(b.params)
         fired = b.fired
-        if len(fired) < n or (len(fired) > n and len({id(p) for p in fired}) < n):
+        if len(fired) < n or len({id(p) for p in fired}) < n:  # (a parameter may fire twice: count distinct ones)
             return False
         if b.missed:
             last = fired[-1]
